@@ -1,0 +1,100 @@
+/* oracle/cf_oracle.h -- CPU restatement of iS3D's smooth Cooper-Frye path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this library.
+ * The product (is3d_b200/csrc) never links or calls it.
+ *
+ * Parity status: PINNED for df_mode 1-4 (mode 1 surfaces, 3+1D and 2+1D) against the unmodified reference sources
+ * compiled here (oracle/_ref/is3d_ref, see oracle/Makefile) -- tests/test_oracle_vs_reference.py and the committed
+ * vectors under tests/golden/.  The anisotropic kernel (cf_oracle_smooth_vah) is pinned against a direct call of the
+ * reference's (otherwise uncalled) calculate_dN_pTdpTdphidy_VAH_PL; its coefficient lookup follows the only
+ * specification that exists (src/cuda/deltafReader.cu:192-277) and is "parity unpinned".
+ * GSL is absent from the image: the natural cubic spline and the 3x3 LU inverse restate GSL's published
+ * algorithms (see oracle/gsl_shim); "parity unpinned" against a real libgsl at the 1e-16 level.
+ */
+#ifndef CF_ORACLE_H
+#define CF_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+  int64_t n_cells;
+  const double *tau, *eta, *dat, *dax, *day, *dan, *ux, *uy, *un, *T, *P, *E;
+  const double *pixx, *pixy, *pixn, *piyy, *piyn, *bulkPi;
+  const double *muB, *nB, *Vx, *Vy, *Vn;
+  /* anisotropic (mode 2) only */
+  const double *pitt, *pitx, *pity, *pitn, *pinn, *Wx, *Wy, *Lambda, *aL, *c0, *c1, *c2, *c3, *c4;
+} cfo_cells;
+
+typedef struct {
+  int32_t n;
+  const double *mass, *sign, *degeneracy, *baryon;
+} cfo_species;
+
+typedef struct {
+  int32_t n_pT, n_phi, n_y, n_eta;       /* table lengths (y table length even in 2+1D) */
+  const double *pT, *phi, *phi_weight, *y, *eta, *eta_weight;
+} cfo_grid;
+
+typedef struct {
+  int32_t df_mode, dimension, include_baryon, include_bulk, include_shear, include_diff, regulate_deltaf, outflow;
+  double deta_min, mass_pion0;
+} cfo_flags;
+
+/* muB = 0 rows of the coefficient tables + the Jonah lambda/z tables */
+typedef struct {
+  int32_t n_T;
+  const double *T, *c0, *c1, *c2, *c3, *c4, *F, *G, *betabulk, *betaV, *betapi;
+  int32_t n_jonah;
+  const double *jonah_x, *jonah_lambda2, *jonah_z;
+  double bulkPi_over_Peq_max;
+} cfo_df_tables;
+
+typedef struct {
+  int32_t n_points;                      /* Gauss-Laguerre points per alpha */
+  const double *root1, *weight1, *root2, *weight2;
+} cfo_laguerre;
+
+/* per-cell coefficient struct, reference readindata.h:105-131 */
+typedef struct {
+  double c0, c1, c2, c3, c4, shear14_coeff, F, G, betabulk, betaV, betapi, lambda, z, delta_lambda, delta_z;
+} cfo_dfcoef;
+
+/* natural cubic spline (GSL cspline restated): c has n entries */
+void cfo_spline_init(const double *x, const double *y, int n, double *c);
+double cfo_spline_eval(const double *x, const double *y, const double *c, int n, double xv, int *err);
+
+/* Deltaf_Data::cubic_spline, deltafReader.cpp:325-395; returns nonzero if T or Pi/P is outside the table */
+int cfo_df_coefficients(const cfo_df_tables *tab, int df_mode, double T, double E, double P, double bulkPi, cfo_dfcoef *out);
+
+/* Deltaf_Data::compute_jonah_coefficients, deltafReader.cpp:222-297: fills x[301], lambda2[301], z[301]; returns max x */
+double cfo_jonah_tables(int n_particles, const double *mass, const double *degeneracy, const double *sign, double T_avg,
+                        const cfo_laguerre *gla, double *x, double *lambda2, double *z);
+
+/* surface averages as in FO_data_reader::read_surf_VH, readindata.cpp:423-466: out[5] = T,E,P,muB,nB */
+void cfo_surface_averages(const cfo_cells *c, double *out5);
+
+/* EmissionFunctionArray::calculate_dN_pTdpTdphidy, emissionfunction_smooth_kernels.cpp:28-393 (df_mode 1,2).
+ * dN is [n_y_tab][n_phi][n_pT][n_species] (species fastest) and is ADDED into.  Returns #cells skipped (u.dsigma<=0)
+ * or a negative error code. */
+int64_t cfo_smooth_vh(const cfo_flags *fl, const cfo_cells *c, const cfo_species *sp, const cfo_grid *g,
+                      const cfo_df_tables *tab, double *dN);
+
+/* EmissionFunctionArray::calculate_dN_ptdptdphidy_feqmod, :396-996 (df_mode 3,4).  *breakdown gets the cell count. */
+int64_t cfo_smooth_feqmod(const cfo_flags *fl, const cfo_cells *c, const cfo_species *sp, const cfo_grid *g,
+                          const cfo_df_tables *tab, const cfo_laguerre *gla, double *dN, int64_t *breakdown);
+
+/* EmissionFunctionArray::calculate_dN_pTdpTdphidy_VAH_PL, :2140-2393 */
+int64_t cfo_smooth_vah(const cfo_flags *fl, const cfo_cells *c, const cfo_species *sp, const cfo_grid *g, double *dN);
+
+/* VAH helpers: aL_fit / R200 (arsenal.cpp:999-1066) and the (Lambda, aL) bilinear lookup of
+ * src/cuda/deltafReader.cu:192-277 */
+double cfo_aL_fit(double pl_over_peq);
+double cfo_R200(double aL);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,206 @@
+"""ctypes binding of oracle/libcf_oracle.so -- TEST INFRASTRUCTURE ONLY.
+
+May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never by the
+product package (is3d_b200/).  Also drives the compiled reference (oracle/_ref/is3d_ref) inside a materialised
+working directory.
+"""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_D = C.POINTER(C.c_double)
+
+CELL_FIELDS = ("tau", "eta", "dat", "dax", "day", "dan", "ux", "uy", "un", "T", "P", "E",
+               "pixx", "pixy", "pixn", "piyy", "piyn", "bulkPi", "muB", "nB", "Vx", "Vy", "Vn",
+               "pitt", "pitx", "pity", "pitn", "pinn", "Wx", "Wy", "Lambda", "aL", "c0", "c1", "c2", "c3", "c4")
+
+
+class Cells(C.Structure):
+    _fields_ = [("n_cells", C.c_int64)] + [(k, _D) for k in CELL_FIELDS]
+
+
+class Species(C.Structure):
+    _fields_ = [("n", C.c_int32), ("mass", _D), ("sign", _D), ("degeneracy", _D), ("baryon", _D)]
+
+
+class Grid(C.Structure):
+    _fields_ = [("n_pT", C.c_int32), ("n_phi", C.c_int32), ("n_y", C.c_int32), ("n_eta", C.c_int32),
+                ("pT", _D), ("phi", _D), ("phi_weight", _D), ("y", _D), ("eta", _D), ("eta_weight", _D)]
+
+
+class Flags(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("df_mode", "dimension", "include_baryon", "include_bulk", "include_shear",
+                                         "include_diff", "regulate_deltaf", "outflow")] + \
+               [("deta_min", C.c_double), ("mass_pion0", C.c_double)]
+
+
+class DfTables(C.Structure):
+    _fields_ = [("n_T", C.c_int32)] + [(k, _D) for k in ("T", "c0", "c1", "c2", "c3", "c4", "F", "G", "betabulk", "betaV", "betapi")] + \
+               [("n_jonah", C.c_int32), ("jonah_x", _D), ("jonah_lambda2", _D), ("jonah_z", _D), ("bulkPi_over_Peq_max", C.c_double)]
+
+
+class Laguerre(C.Structure):
+    _fields_ = [("n_points", C.c_int32), ("root1", _D), ("weight1", _D), ("root2", _D), ("weight2", _D)]
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libcf_oracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.cfo_smooth_vh.restype = C.c_int64
+        L.cfo_smooth_feqmod.restype = C.c_int64
+        L.cfo_smooth_vah.restype = C.c_int64
+        L.cfo_jonah_tables.restype = C.c_double
+        L.cfo_aL_fit.restype = C.c_double; L.cfo_aL_fit.argtypes = [C.c_double]
+        L.cfo_R200.restype = C.c_double; L.cfo_R200.argtypes = [C.c_double]
+        L.cfo_spline_eval.restype = C.c_double
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(_D)
+
+
+class _Keep(list):
+    """keeps numpy arrays alive for the duration of a call"""
+
+    def arr(self, x):
+        a = np.ascontiguousarray(x, dtype=np.float64)
+        self.append(a)
+        return _p(a)
+
+
+def _cells(keep, cells):
+    st = Cells()
+    n = len(cells["tau"])
+    st.n_cells = n
+    for k in CELL_FIELDS:
+        if k in cells and cells[k] is not None:
+            setattr(st, k, keep.arr(cells[k]))
+    return st
+
+
+def _species(keep, sp):
+    st = Species()
+    st.n = len(sp["mass"])
+    for k in ("mass", "sign", "degeneracy", "baryon"):
+        setattr(st, k, keep.arr(sp[k]))
+    return st
+
+
+def _grid(keep, g):
+    st = Grid()
+    st.n_pT, st.n_phi, st.n_y, st.n_eta = len(g["pT"]), len(g["phi"]), len(g["y"]), len(g["eta"])
+    for k in ("pT", "phi", "phi_weight", "y", "eta", "eta_weight"):
+        setattr(st, k, keep.arr(g[k]))
+    return st
+
+
+def _flags(fl):
+    st = Flags()
+    for k, _ in Flags._fields_:
+        setattr(st, k, fl[k])
+    return st
+
+
+def _tables(keep, tab):
+    st = DfTables()
+    st.n_T = len(tab["T"])
+    for k in ("T", "c0", "c1", "c2", "c3", "c4", "F", "G", "betabulk", "betaV", "betapi"):
+        setattr(st, k, keep.arr(tab[k]))
+    if tab.get("jonah_x") is not None:
+        st.n_jonah = len(tab["jonah_x"])
+        st.jonah_x = keep.arr(tab["jonah_x"]); st.jonah_lambda2 = keep.arr(tab["jonah_lambda2"]); st.jonah_z = keep.arr(tab["jonah_z"])
+        st.bulkPi_over_Peq_max = tab["bulkPi_over_Peq_max"]
+    return st
+
+
+def _laguerre(keep, gla):
+    st = Laguerre()
+    st.n_points = len(gla["root1"])
+    for k in ("root1", "weight1", "root2", "weight2"):
+        setattr(st, k, keep.arr(gla[k]))
+    return st
+
+
+def n_bins(sp, g):
+    return len(sp["mass"]) * len(g["pT"]) * len(g["phi"]) * len(g["y"])
+
+
+def surface_averages(cells):
+    keep = _Keep(); out = np.zeros(5)
+    st = _cells(keep, cells)
+    lib().cfo_surface_averages(C.byref(st), _p(out))
+    return out
+
+
+def jonah_tables(mass, degeneracy, sign, T_avg, gla):
+    keep = _Keep()
+    x = np.zeros(301); l2 = np.zeros(301); z = np.zeros(301)
+    g = _laguerre(keep, gla)
+    mx = lib().cfo_jonah_tables(C.c_int(len(mass)), keep.arr(mass), keep.arr(degeneracy), keep.arr(sign), C.c_double(T_avg),
+                                C.byref(g), _p(x), _p(l2), _p(z))
+    return dict(jonah_x=x, jonah_lambda2=l2, jonah_z=z, bulkPi_over_Peq_max=mx)
+
+
+def smooth(flags, cells, species, grid, tables=None, laguerre=None, vah=False):
+    """Run the matching oracle kernel; returns (dN flat [y][phi][pT][species], skipped, breakdown)."""
+    keep = _Keep()
+    dN = np.zeros(n_bins(species, grid))
+    fl = _flags(flags); c = _cells(keep, cells); sp = _species(keep, species); g = _grid(keep, grid)
+    bd = C.c_int64(0)
+    if vah:
+        rc = lib().cfo_smooth_vah(C.byref(fl), C.byref(c), C.byref(sp), C.byref(g), _p(dN))
+    elif flags["df_mode"] in (1, 2):
+        t = _tables(keep, tables)
+        rc = lib().cfo_smooth_vh(C.byref(fl), C.byref(c), C.byref(sp), C.byref(g), C.byref(t), _p(dN))
+    else:
+        t = _tables(keep, tables); la = _laguerre(keep, laguerre)
+        rc = lib().cfo_smooth_feqmod(C.byref(fl), C.byref(c), C.byref(sp), C.byref(g), C.byref(t), C.byref(la), _p(dN), C.byref(bd))
+    if rc < 0:
+        raise RuntimeError("cf_oracle error %d" % rc)
+    return dN, int(rc), int(bd.value)
+
+
+# --------------------------------------------------------------------------- compiled reference (oracle/_ref)
+def ref_binary(omp=False):
+    p = os.path.join(_HERE, "_ref", "is3d_ref_omp" if omp else "is3d_ref")
+    return p if os.path.exists(p) else None
+
+
+def run_reference(workdir, what="kernel", omp=False, threads=None, timeout=3600):
+    """Run oracle/_ref/is3d_ref inside `workdir`; returns (dN flat, info dict incl. seconds, mcid, breakdown)."""
+    exe = ref_binary(omp)
+    if exe is None:
+        raise FileNotFoundError("oracle/_ref not built (run `make -C oracle ref` where /root/reference exists)")
+    env = dict(os.environ)
+    if threads:
+        env["OMP_NUM_THREADS"] = str(threads)
+    out = os.path.join(workdir, "results", "dN_raw.bin")
+    r = subprocess.run([exe, what, out], cwd=workdir, capture_output=True, text=True, env=env, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError("reference failed (%d): %s\n%s" % (r.returncode, r.stdout[-2000:], r.stderr[-2000:]))
+    info = None
+    for line in r.stdout.splitlines():
+        if line.startswith("REF_JSON "):
+            info = json.loads(line[len("REF_JSON "):])
+        if "feqmod breaks down for" in line:
+            bd = int(line.split("feqmod breaks down for")[1].split()[0])
+    if info is None:
+        raise RuntimeError("reference printed no REF_JSON line:\n" + r.stdout[-2000:])
+    info["breakdown"] = locals().get("bd", 0)
+    info["stdout"] = r.stdout
+    return np.fromfile(out), info
