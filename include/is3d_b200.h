@@ -1,0 +1,130 @@
+/* include/is3d_b200.h -- C ABI of the B200-native smooth Cooper-Frye spectra path.
+ *
+ * The reference (derekeverett/iS3D) has no FFI/plugin interface; the hot path sits behind the C++ member functions
+ *   EmissionFunctionArray::calculate_dN_pTdpTdphidy          src/cpp/emissionfunction.h:179, emissionfunction_smooth_kernels.cpp:28
+ *   EmissionFunctionArray::calculate_dN_ptdptdphidy_feqmod   src/cpp/emissionfunction.h:182, emissionfunction_smooth_kernels.cpp:396
+ *   EmissionFunctionArray::calculate_dN_pTdpTdphidy_VAH_PL   src/cpp/emissionfunction.h:(VAH_PL), emissionfunction_smooth_kernels.cpp:2140
+ * called from EmissionFunctionArray::calculate_spectra (src/cpp/emissionfunction.cpp:1519, 1584, 1650).  The entry
+ * points below take what those calls take -- the per-species arrays, the structure-of-arrays freeze-out surface, the
+ * momentum tables and the delta-f coefficient tables -- as plain pointers and sizes, and add the result into a
+ * caller-owned spectra array with the reference's layout.  INTEGRATION.md shows the few lines that replace the three
+ * call sites.  No C++/torch types cross this boundary; all functions return 0 or an IS3D_ERR_* code, never exit().
+ *
+ * Threading: one calling host thread per process/GPU.  Multi-GPU runs use one process per GPU, each calling with its
+ * own contiguous shard of cells; the caller sums the spectra arrays (one all-reduce).
+ */
+#ifndef IS3D_B200_H
+#define IS3D_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  IS3D_OK = 0,
+  IS3D_ERR_ARGUMENT = 1,      /* NULL / inconsistent argument */
+  IS3D_ERR_UNSUPPORTED = 2,   /* flag combination outside the path (e.g. include_baryon = 1) */
+  IS3D_ERR_TABLE_RANGE = 3,   /* a cell's T (or Pi/P for df_mode 4) lies outside the coefficient table; the reference aborts here */
+  IS3D_ERR_CUDA = 4,          /* CUDA runtime failure; is3d_b200_last_error() has the text */
+  IS3D_ERR_NO_DEVICE = 5,     /* no CUDA device: there is deliberately no CPU fallback */
+  IS3D_ERR_IO = 6             /* host layer: missing / malformed input file */
+};
+
+/* Freeze-out surface, structure of arrays, GeV / fm units exactly as EmissionFunctionArray::calculate_spectra packs
+ * them (emissionfunction.cpp:1327-1499).  Pointers for switched-off terms may be NULL.  Read-only, caller-owned. */
+typedef struct {
+  int64_t n_cells;
+  const double *tau, *eta, *dat, *dax, *day, *dan, *ux, *uy, *un, *T, *P, *E;
+  const double *pixx, *pixy, *pixn, *piyy, *piyn, *bulkPi;
+  const double *muB, *nB, *Vx, *Vy, *Vn;
+  /* anisotropic hydro (mode 2) only: all ten pi_perp components, W_perp, Lambda, alpha_L and per-cell c0..c4 */
+  const double *pitt, *pitx, *pity, *pitn, *pinn, *Wx, *Wy, *Lambda, *aL, *c0, *c1, *c2, *c3, *c4;
+} is3d_surface;
+
+/* Chosen species in output order (emissionfunction.cpp:1293-1307). */
+typedef struct {
+  int32_t n;
+  const double *mass, *sign, *degeneracy, *baryon;
+} is3d_species;
+
+/* Momentum / rapidity tables (iS3D.cpp:161-167).  eta/eta_weight are used when dimension = 2, y when dimension = 3. */
+typedef struct {
+  int32_t n_pT, n_phi, n_y, n_eta;
+  const double *pT, *phi, *y, *eta, *eta_weight;
+} is3d_grid;
+
+/* Switches captured by the EmissionFunctionArray constructor (emissionfunction.cpp:170-191). */
+typedef struct {
+  int32_t mode;              /* surface type: 0,1,4,5,6,7 = viscous hydro; 2 = anisotropic hydro, PL matching */
+  int32_t df_mode;           /* 1 14-moment, 2 Chapman-Enskog, 3 feqmod (Mike), 4 feqmod (Jonah) */
+  int32_t dimension;         /* 2 boost invariant (y = 0, eta quadrature) or 3 */
+  int32_t include_baryon, include_bulk_deltaf, include_shear_deltaf, include_baryondiff_deltaf;
+  int32_t regulate_deltaf, outflow;
+  double deta_min, mass_pion0;
+} is3d_flags;
+
+/* muB = 0 rows of deltaf_coefficients/vh/<eos>/{c0..c4,F,G,betabulk,betaV,betapi}.dat as stored in the files
+ * (T-scaled; deltafReader.cpp:65-219), plus the Jonah lambda^2 / z tables (deltafReader.cpp:222-297). */
+typedef struct {
+  int32_t n_T;
+  const double *T, *c0, *c1, *c2, *c3, *c4, *F, *G, *betabulk, *betaV, *betapi;
+  int32_t n_jonah;
+  const double *jonah_x, *jonah_lambda2, *jonah_z;
+  double bulkPi_over_Peq_max;
+} is3d_df_tables;
+
+/* generalized Gauss-Laguerre nodes alpha = 1, 2 (tables/gla_roots_weights_32_points.txt), feqmod only */
+typedef struct {
+  int32_t n_points;
+  const double *root1, *weight1, *root2, *weight2;
+} is3d_laguerre;
+
+typedef struct {
+  int32_t memory;            /* 0: surface arrays and dN live in host memory; 1: they are device pointers on the current device */
+  void *stream;              /* cudaStream_t to launch on (NULL = default stream) */
+  int32_t n_chunks;          /* cell-range split used for load balance; 0 = choose */
+  int32_t tile_variant;      /* kernel register-tile variant; 0 = default */
+  int32_t reserved[4];
+} is3d_options;
+
+typedef struct {
+  int64_t cells_skipped_udsigma;   /* cells with u.dsigma <= 0 (smooth_kernels.cpp:137) */
+  int64_t cells_feqmod_breakdown;  /* the reference's `breakdown` counter (smooth_kernels.cpp:721, 992) */
+  int64_t evaluations;             /* cells x species x pT x phi x y x eta */
+  double h2d_ms, prepare_ms, kernel_ms, reduce_ms, d2h_ms, total_ms;   /* CUDA-event times on the launch stream */
+  int32_t gpu_launches;            /* kernels launched by this call */
+  int32_t n_chunks, tile_variant;
+} is3d_stats;
+
+/* Bind to the current CUDA device and create the workspace.  Safe to call more than once. */
+int is3d_b200_init(void);
+int is3d_b200_shutdown(void);
+const char *is3d_b200_strerror(int code);
+const char *is3d_b200_last_error(void);
+int is3d_b200_version(void);
+
+/* dN_out has n_species * n_pT * n_phi * n_y doubles, index ipart + n_species*(ipT + n_pT*(iphi + n_phi*iy))
+ * (emissionfunction_smooth_kernels.cpp:363); the result is ADDED into it (reference: `+=` into a zeroed array).
+ * Dispatch follows calculate_spectra: mode 2 -> anisotropic kernel; df_mode 1,2 -> linear delta-f; 3,4 -> feqmod. */
+int is3d_b200_smooth_spectra(const is3d_flags *flags, const is3d_surface *surface, const is3d_species *species,
+                             const is3d_grid *grid, const is3d_df_tables *df, const is3d_laguerre *laguerre,
+                             const is3d_options *options, double *dN_out, is3d_stats *stats);
+
+/* FP64 FMA peak of the current device measured with a dependency-free DFMA chain (the roofline denominator;
+ * MEASURED_PEAKS.json carries no FP64 figure).  Returns TFLOP/s in *tflops, SM clock not touched. */
+int is3d_b200_measure_fp64_peak(double *tflops, double *ms);
+/* Same probe launched back to back for `seconds` of device time: the sustained (power-capped) FP64 roof. */
+int is3d_b200_measure_fp64_sustained(double seconds, double *tflops);
+
+/* ---- host layer: the drop-in behind iS3D_parameters.dat / input/surface.dat / PDG / deltaf_coefficients / tables ----
+ * Equivalent of IS3D::run_particlization(1) with operation = 1 (src/cpp/iS3D.cpp:73-191): reads the CWD-relative input
+ * files under `workdir`, runs the spectra on the GPU, writes results/dN_pTdpTdphidy*.dat, results/vn_continuous/ and
+ * results/dN_dy_*.dat with the reference's formats.  If dN_raw != NULL it receives the spectra (n_raw doubles max). */
+int is3d_b200_run_workdir(const char *workdir, double *dN_raw, int64_t n_raw, int32_t *mcid_out, int32_t n_mcid_max,
+                          is3d_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,223 @@
+"""ctypes binding of the C ABI in include/is3d_b200.h (is3d_b200/libis3d_b200.so).
+
+This is the host-side mirror used by tests, bench.py and the torch.distributed driver: it only marshals pointers.
+The library is built in-tree by `is3d_b200.build`; if it is missing, or no CUDA device is present, calls fail loudly
+-- there is no CPU fallback anywhere in this package.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libis3d_b200.so")
+_D = C.POINTER(C.c_double)
+
+SURFACE_FIELDS = ("tau", "eta", "dat", "dax", "day", "dan", "ux", "uy", "un", "T", "P", "E",
+                  "pixx", "pixy", "pixn", "piyy", "piyn", "bulkPi", "muB", "nB", "Vx", "Vy", "Vn",
+                  "pitt", "pitx", "pity", "pitn", "pinn", "Wx", "Wy", "Lambda", "aL", "c0", "c1", "c2", "c3", "c4")
+DF_FIELDS = ("T", "c0", "c1", "c2", "c3", "c4", "F", "G", "betabulk", "betaV", "betapi")
+
+ERRORS = {0: "IS3D_OK", 1: "IS3D_ERR_ARGUMENT", 2: "IS3D_ERR_UNSUPPORTED", 3: "IS3D_ERR_TABLE_RANGE", 4: "IS3D_ERR_CUDA",
+          5: "IS3D_ERR_NO_DEVICE", 6: "IS3D_ERR_IO"}
+
+
+class Surface(C.Structure):
+    _fields_ = [("n_cells", C.c_int64)] + [(k, _D) for k in SURFACE_FIELDS]
+
+
+class Species(C.Structure):
+    _fields_ = [("n", C.c_int32), ("mass", _D), ("sign", _D), ("degeneracy", _D), ("baryon", _D)]
+
+
+class Grid(C.Structure):
+    _fields_ = [("n_pT", C.c_int32), ("n_phi", C.c_int32), ("n_y", C.c_int32), ("n_eta", C.c_int32),
+                ("pT", _D), ("phi", _D), ("y", _D), ("eta", _D), ("eta_weight", _D)]
+
+
+class Flags(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("mode", "df_mode", "dimension", "include_baryon", "include_bulk_deltaf",
+                                         "include_shear_deltaf", "include_baryondiff_deltaf", "regulate_deltaf", "outflow")] + \
+               [("deta_min", C.c_double), ("mass_pion0", C.c_double)]
+
+
+class DfTables(C.Structure):
+    _fields_ = [("n_T", C.c_int32)] + [(k, _D) for k in DF_FIELDS] + \
+               [("n_jonah", C.c_int32), ("jonah_x", _D), ("jonah_lambda2", _D), ("jonah_z", _D),
+                ("bulkPi_over_Peq_max", C.c_double)]
+
+
+class Laguerre(C.Structure):
+    _fields_ = [("n_points", C.c_int32), ("root1", _D), ("weight1", _D), ("root2", _D), ("weight2", _D)]
+
+
+class Options(C.Structure):
+    _fields_ = [("memory", C.c_int32), ("stream", C.c_void_p), ("n_chunks", C.c_int32), ("tile_variant", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("cells_skipped_udsigma", C.c_int64), ("cells_feqmod_breakdown", C.c_int64), ("evaluations", C.c_int64),
+                ("h2d_ms", C.c_double), ("prepare_ms", C.c_double), ("kernel_ms", C.c_double), ("reduce_ms", C.c_double),
+                ("d2h_ms", C.c_double), ("total_ms", C.c_double), ("gpu_launches", C.c_int32), ("n_chunks", C.c_int32),
+                ("tile_variant", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Is3dError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("%s (%d): %s" % (ERRORS.get(code, "?"), code, text))
+        self.code = code
+
+
+_LIB = None
+
+
+def lib():
+    """Load libis3d_b200.so; raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError("%s is missing: run `python -m is3d_b200.build` (needs nvcc)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.is3d_b200_strerror.restype = C.c_char_p
+        L.is3d_b200_last_error.restype = C.c_char_p
+        L.is3d_b200_smooth_spectra.restype = C.c_int
+        L.is3d_b200_smooth_spectra.argtypes = [C.POINTER(Flags), C.POINTER(Surface), C.POINTER(Species), C.POINTER(Grid),
+                                               C.POINTER(DfTables), C.POINTER(Laguerre), C.POINTER(Options), C.c_void_p,
+                                               C.POINTER(Stats)]
+        L.is3d_b200_measure_fp64_peak.argtypes = [_D, _D]
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise Is3dError(rc, lib().is3d_b200_last_error().decode() or lib().is3d_b200_strerror(rc).decode())
+
+
+def init():
+    _check(lib().is3d_b200_init())
+
+
+def shutdown():
+    _check(lib().is3d_b200_shutdown())
+
+
+def measure_fp64_peak():
+    t = C.c_double(0); ms = C.c_double(0)
+    _check(lib().is3d_b200_measure_fp64_peak(C.byref(t), C.byref(ms)))
+    return t.value, ms.value
+
+
+def measure_fp64_sustained(seconds=3.0):
+    t = C.c_double(0)
+    _check(lib().is3d_b200_measure_fp64_sustained(C.c_double(seconds), C.byref(t)))
+    return t.value
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+class _Marshal:
+    """Turns numpy arrays / torch tensors into double* and keeps them alive."""
+
+    def __init__(self, device):
+        self.keep = []
+        self.device = device
+
+    def host(self, x):
+        a = np.ascontiguousarray(x, dtype=np.float64)
+        self.keep.append(a)
+        return a.ctypes.data_as(_D)
+
+    def cells(self, x):
+        if self.device:
+            if not _is_torch(x) or not x.is_cuda:
+                raise TypeError("memory='device' needs CUDA tensors for the surface arrays")
+            import torch
+            t = x.contiguous()
+            if t.dtype != torch.float64:
+                raise TypeError("surface tensors must be float64")
+            self.keep.append(t)
+            return C.cast(C.c_void_p(t.data_ptr()), _D)
+        if _is_torch(x):
+            x = x.detach().cpu().numpy()
+        return self.host(x)
+
+
+def make_flags(flags, mode=1):
+    f = Flags()
+    f.mode = flags.get("mode", mode)
+    f.df_mode = flags["df_mode"]; f.dimension = flags["dimension"]
+    f.include_baryon = flags.get("include_baryon", 0)
+    f.include_bulk_deltaf = flags.get("include_bulk", flags.get("include_bulk_deltaf", 1))
+    f.include_shear_deltaf = flags.get("include_shear", flags.get("include_shear_deltaf", 1))
+    f.include_baryondiff_deltaf = flags.get("include_diff", flags.get("include_baryondiff_deltaf", 0))
+    f.regulate_deltaf = flags.get("regulate_deltaf", 1); f.outflow = flags.get("outflow", 1)
+    f.deta_min = flags.get("deta_min", 1.0e-5); f.mass_pion0 = flags.get("mass_pion0", 0.138)
+    return f
+
+
+def smooth_spectra(flags, cells, species, grid, df_tables=None, laguerre=None, out=None, memory="host",
+                   stream=None, n_chunks=0, tile_variant=0):
+    """Call is3d_b200_smooth_spectra.
+
+    cells: dict of per-cell arrays (numpy for memory='host', float64 CUDA tensors for memory='device').
+    Returns (dN, stats dict); dN is flat [y][phi][pT][species] (species fastest), numpy or the CUDA tensor `out`.
+    The result is ADDED into `out` when given.
+    """
+    device = (memory == "device")
+    m = _Marshal(device)
+    sf = Surface()
+    n = len(cells["tau"]) if not _is_torch(cells["tau"]) else int(cells["tau"].numel())
+    sf.n_cells = n
+    for k in SURFACE_FIELDS:
+        if k in cells and cells[k] is not None:
+            setattr(sf, k, m.cells(cells[k]))
+    sp = Species(); sp.n = len(species["mass"])
+    for k in ("mass", "sign", "degeneracy", "baryon"):
+        setattr(sp, k, m.host(species[k]))
+    g = Grid()
+    g.n_pT, g.n_phi, g.n_y, g.n_eta = len(grid["pT"]), len(grid["phi"]), len(grid["y"]), len(grid["eta"])
+    for k in ("pT", "phi", "y", "eta", "eta_weight"):
+        setattr(g, k, m.host(grid[k]))
+    dft = DfTables()
+    if df_tables is not None:
+        dft.n_T = len(df_tables["T"])
+        for k in DF_FIELDS:
+            if df_tables.get(k) is not None:
+                setattr(dft, k, m.host(df_tables[k]))
+        if df_tables.get("jonah_x") is not None:
+            dft.n_jonah = len(df_tables["jonah_x"])
+            dft.jonah_x = m.host(df_tables["jonah_x"]); dft.jonah_lambda2 = m.host(df_tables["jonah_lambda2"])
+            dft.jonah_z = m.host(df_tables["jonah_z"]); dft.bulkPi_over_Peq_max = float(df_tables["bulkPi_over_Peq_max"])
+    la = Laguerre()
+    if laguerre is not None:
+        la.n_points = len(laguerre["root1"])
+        for k in ("root1", "weight1", "root2", "weight2"):
+            setattr(la, k, m.host(laguerre[k]))
+    n_bins = sp.n * g.n_pT * g.n_phi * g.n_y
+    if device:
+        import torch
+        if out is None:
+            out = torch.zeros(n_bins, dtype=torch.float64, device=cells["tau"].device)
+        out_ptr = C.c_void_p(out.data_ptr())
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+    else:
+        if out is None:
+            out = np.zeros(n_bins)
+        assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.size == n_bins
+        out_ptr = C.c_void_p(out.ctypes.data)
+    opt = Options(); opt.memory = 1 if device else 0
+    opt.stream = C.c_void_p(stream or 0); opt.n_chunks = n_chunks; opt.tile_variant = tile_variant
+    st = Stats()
+    fl = make_flags(flags)
+    rc = lib().is3d_b200_smooth_spectra(C.byref(fl), C.byref(sf), C.byref(sp), C.byref(g), C.byref(dft), C.byref(la),
+                                        C.byref(opt), out_ptr, C.byref(st))
+    _check(rc)
+    return out, st.as_dict()

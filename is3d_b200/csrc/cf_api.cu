@@ -1,0 +1,369 @@
+// cf_api.cu -- the extern "C" boundary (include/is3d_b200.h): workspace management, host<->device staging, kernel
+// sequencing and CUDA-event timing.  There is no CPU fallback: without a CUDA device every entry point fails.
+#include "cf_internal.h"
+#include "host_math.h"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace is3d {
+
+static std::mutex g_mutex;
+static std::string g_last_error;
+static bool g_init = false;
+static int g_sm_count = 0;
+
+#define CU_CHECK(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      char buf__[512];                                                                          \
+      snprintf(buf__, sizeof(buf__), "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      g_last_error = buf__;                                                                     \
+      return IS3D_ERR_CUDA;                                                                     \
+    }                                                                                           \
+  } while (0)
+
+// a grow-only device buffer
+struct DevBuf {
+  void *p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t bytes)
+  {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct Workspace {
+  DevBuf raw, small, Y, P, S, partial, dN, counters, extra;
+  cudaEvent_t ev[8];
+  bool events = false;
+  void release()
+  {
+    raw.release(); small.release(); Y.release(); P.release(); S.release(); partial.release(); dN.release();
+    counters.release(); extra.release();
+    if (events) { for (auto &e : ev) cudaEventDestroy(e); events = false; }
+  }
+};
+static Workspace g_ws;
+
+// bump allocator over the `small` buffer for tables; all offsets 256-byte aligned
+struct SmallArena {
+  std::vector<unsigned char> host;
+  size_t put(const double *src, size_t n)
+  {
+    size_t off = (host.size() + 255) & ~(size_t)255;
+    host.resize(off + n * sizeof(double));
+    if (n) memcpy(host.data() + off, src, n * sizeof(double));
+    return off;
+  }
+};
+
+static int fail(int code, const char *msg) { g_last_error = msg; return code; }
+
+}  // namespace is3d
+
+using namespace is3d;
+
+extern "C" {
+
+int is3d_b200_version(void) { return 100; }
+
+const char *is3d_b200_strerror(int code)
+{
+  switch (code) {
+    case IS3D_OK: return "ok";
+    case IS3D_ERR_ARGUMENT: return "invalid argument";
+    case IS3D_ERR_UNSUPPORTED: return "flag combination not supported by the smooth Cooper-Frye path";
+    case IS3D_ERR_TABLE_RANGE: return "cell temperature or Pi/P outside the delta-f coefficient table";
+    case IS3D_ERR_CUDA: return "CUDA runtime error";
+    case IS3D_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case IS3D_ERR_IO: return "input/output error in the host layer";
+    default: return "unknown error";
+  }
+}
+
+const char *is3d_b200_last_error(void) { return g_last_error.c_str(); }
+
+int is3d_b200_init(void)
+{
+  std::lock_guard<std::mutex> lk(g_mutex);
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return fail(IS3D_ERR_NO_DEVICE, "no CUDA device visible");
+  int dev = 0;
+  CU_CHECK(cudaGetDevice(&dev));
+  CU_CHECK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+  if (!g_ws.events) {
+    for (auto &e : g_ws.ev) CU_CHECK(cudaEventCreate(&e));
+    g_ws.events = true;
+  }
+  g_init = true;
+  return IS3D_OK;
+}
+
+int is3d_b200_shutdown(void)
+{
+  std::lock_guard<std::mutex> lk(g_mutex);
+  g_ws.release();
+  g_init = false;
+  return IS3D_OK;
+}
+
+int is3d_b200_measure_fp64_peak(double *tflops, double *ms_out)
+{
+  int rc = is3d_b200_init();
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g_mutex);
+  CU_CHECK(g_ws.counters.reserve(256));
+  int blocks = 0, threads = 0; long long per_thread = 0;
+  const int iters = 20000;
+  CU_CHECK(launch_fp64_peak(g_ws.counters.as<double>(), 2000, 0, &blocks, &threads, &per_thread));   // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    CU_CHECK(cudaEventRecord(g_ws.ev[0], 0));
+    CU_CHECK(launch_fp64_peak(g_ws.counters.as<double>(), iters, 0, &blocks, &threads, &per_thread));
+    CU_CHECK(cudaEventRecord(g_ws.ev[1], 0));
+    CU_CHECK(cudaEventSynchronize(g_ws.ev[1]));
+    float ms = 0;
+    CU_CHECK(cudaEventElapsedTime(&ms, g_ws.ev[0], g_ws.ev[1]));
+    if (ms < best) best = ms;
+  }
+  const double flops = 2.0 * (double)per_thread * blocks * threads;
+  if (tflops) *tflops = flops / (best * 1e-3) * 1e-12;
+  if (ms_out) *ms_out = best;
+  return IS3D_OK;
+}
+
+int is3d_b200_measure_fp64_sustained(double seconds, double *tflops)
+{
+  int rc = is3d_b200_init();
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g_mutex);
+  CU_CHECK(g_ws.counters.reserve(256));
+  int blocks = 0, threads = 0; long long per_thread = 0;
+  const int iters = 20000;                       // ~21 ms per launch at the burst clock
+  CU_CHECK(launch_fp64_peak(g_ws.counters.as<double>(), 2000, 0, &blocks, &threads, &per_thread));
+  CU_CHECK(cudaDeviceSynchronize());
+  int launches = (int)(seconds / 0.021) + 1;
+  CU_CHECK(cudaEventRecord(g_ws.ev[0], 0));
+  for (int i = 0; i < launches; i++) CU_CHECK(launch_fp64_peak(g_ws.counters.as<double>(), iters, 0, &blocks, &threads, &per_thread));
+  CU_CHECK(cudaEventRecord(g_ws.ev[1], 0));
+  CU_CHECK(cudaEventSynchronize(g_ws.ev[1]));
+  float ms = 0;
+  CU_CHECK(cudaEventElapsedTime(&ms, g_ws.ev[0], g_ws.ev[1]));
+  const double flops = 2.0 * (double)per_thread * blocks * threads * launches;
+  if (tflops) *tflops = flops / (ms * 1e-3) * 1e-12;
+  return IS3D_OK;
+}
+
+int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const is3d_species *sp, const is3d_grid *gr,
+                             const is3d_df_tables *df, const is3d_laguerre *gla, const is3d_options *opt_in,
+                             double *dN_out, is3d_stats *stats)
+{
+  if (!fl || !sf || !sp || !gr || !dN_out) return fail(IS3D_ERR_ARGUMENT, "NULL argument");
+  if (!g_init) { int rc = is3d_b200_init(); if (rc) return rc; }
+  std::lock_guard<std::mutex> lk(g_mutex);
+  is3d_options opt; memset(&opt, 0, sizeof(opt));
+  if (opt_in) opt = *opt_in;
+  cudaStream_t st = (cudaStream_t)opt.stream;
+  is3d_stats stt; memset(&stt, 0, sizeof(stt));
+
+  // ---- validation / dispatch (emissionfunction.cpp:1503-1673)
+  const bool vah = (fl->mode == 2);
+  if (fl->dimension != 2 && fl->dimension != 3) return fail(IS3D_ERR_ARGUMENT, "dimension must be 2 or 3");
+  if (sp->n <= 0 || gr->n_pT <= 0 || gr->n_phi <= 0 || gr->n_y <= 0) return fail(IS3D_ERR_ARGUMENT, "empty species list or momentum table");
+  if (fl->dimension == 2 && (gr->n_eta <= 0 || !gr->eta || !gr->eta_weight)) return fail(IS3D_ERR_ARGUMENT, "dimension = 2 needs the eta table");
+  if (fl->include_baryon) return fail(IS3D_ERR_UNSUPPORTED, "include_baryon = 1 (the reference's (T, muB) lookup reads out of bounds, SURVEY R8)");
+  if (vah) return fail(IS3D_ERR_UNSUPPORTED, "mode 2 (anisotropic) kernel not built yet");
+  if (fl->df_mode != 1 && fl->df_mode != 2) return fail(IS3D_ERR_UNSUPPORTED, "df_mode 3/4 (feqmod) kernel not built yet");
+  if (!df || df->n_T < 3) return fail(IS3D_ERR_ARGUMENT, "delta-f coefficient tables missing");
+  const int64_t n_cells = sf->n_cells;
+  if (n_cells < 0) return fail(IS3D_ERR_ARGUMENT, "negative cell count");
+  const bool dim2 = (fl->dimension == 2);
+  const int64_t n_bins = (int64_t)sp->n * gr->n_pT * gr->n_phi * gr->n_y;
+
+  // ---- layout
+  Layout L; memset(&L, 0, sizeof(L));
+  L.n_species = sp->n; L.n_pT = gr->n_pT; L.n_phi = gr->n_phi; L.n_y_out = gr->n_y;
+  L.dim2 = dim2 ? 1 : 0;
+  L.n_slots = dim2 ? gr->n_eta : gr->n_y;
+  int variant = opt.tile_variant;
+  if (variant < 0 || variant > 7) variant = 0;
+  int nyt, npt, ct;
+  hot_variant_shape(variant, L.dim2, &nyt, &npt, &ct);
+  L.nst = dim2 ? L.n_slots : nyt;
+  L.n_ytiles = dim2 ? 1 : (L.n_slots + nyt - 1) / nyt;
+  L.npt = npt; L.n_ptiles = (L.n_phi + npt - 1) / npt;
+  L.ct = ct;
+  L.n_cells = n_cells;
+  L.n_tiles = (n_cells + ct - 1) / ct;
+  L.n_cells_pad = L.n_tiles * ct;
+
+  const int n_pairs = sp->n * gr->n_pT;
+  const int n_groups = (n_pairs + 31) / 32;
+  int n_warps = kMaxWarps;                                  // widest block whose padding wastes <= 4 % of the warps
+  {
+    int best = 1 << 30;
+    for (int w = kMaxWarps; w >= 1; w--) {
+      const int launched = ((n_groups + w - 1) / w) * w;
+      if ((launched - n_groups) * 25 <= launched) { n_warps = w; break; }
+      if (launched < best) { best = launched; n_warps = w; }
+    }
+  }
+  const int n_groupblocks = (n_groups + n_warps - 1) / n_warps;
+  const int64_t n_bintiles = (int64_t)n_groupblocks * L.n_ytiles * L.n_ptiles;
+  int n_chunks = opt.n_chunks;
+  if (n_chunks <= 0) {
+    const int64_t target_blocks = (int64_t)g_sm_count * 96;             // >= 16 waves at 6 blocks/SM: small tail
+    n_chunks = (int)((target_blocks + n_bintiles - 1) / n_bintiles);
+    const int64_t max_partial_bytes = (int64_t)2 << 30;                 // keep the partial buffer <= 2 GiB
+    int64_t cap = max_partial_bytes / (n_bins * 8 > 0 ? n_bins * 8 : 1);
+    if (cap < 1) cap = 1;
+    if (n_chunks > cap) n_chunks = (int)cap;
+  }
+  if ((int64_t)n_chunks > L.n_tiles) n_chunks = (int)(L.n_tiles > 0 ? L.n_tiles : 1);
+  if (n_chunks < 1) n_chunks = 1;
+  if (n_bintiles * n_chunks > 2147483647LL) return fail(IS3D_ERR_ARGUMENT, "grid too large");
+
+  // ---- small tables -> one staging buffer
+  SmallArena ar;
+  std::vector<double> cosphi(gr->n_phi), sinphi(gr->n_phi);
+  for (int k = 0; k < gr->n_phi; k++) { cosphi[k] = cos(gr->phi[k]); sinphi[k] = sin(gr->phi[k]); }   // smooth_kernels.cpp:43-48
+  const size_t o_mass = ar.put(sp->mass, sp->n), o_sign = ar.put(sp->sign, sp->n), o_deg = ar.put(sp->degeneracy, sp->n);
+  const size_t o_pT = ar.put(gr->pT, gr->n_pT), o_cos = ar.put(cosphi.data(), gr->n_phi), o_sin = ar.put(sinphi.data(), gr->n_phi);
+  const size_t o_sloty = dim2 ? ar.put(gr->eta, gr->n_eta) : ar.put(gr->y, gr->n_y);
+  const size_t o_slotw = dim2 ? ar.put(gr->eta_weight, gr->n_eta) : 0;
+  const size_t o_T = ar.put(df->T, df->n_T);
+  struct SplineOff { size_t y, c; };
+  auto put_spline = [&](const double *y) {
+    SplineOff o{0, 0};
+    if (!y) return o;
+    std::vector<double> c(df->n_T);
+    host_spline_init(df->T, y, df->n_T, c.data());
+    o.y = ar.put(y, df->n_T); o.c = ar.put(c.data(), df->n_T);
+    return o;
+  };
+  const SplineOff s_c0 = put_spline(df->c0), s_c2 = put_spline(df->c2), s_F = put_spline(df->F),
+                  s_bb = put_spline(df->betabulk), s_bp = put_spline(df->betapi);
+
+  // ---- device buffers
+  const int n_raw = 18;
+  const double *raw_src[n_raw] = {sf->tau, sf->eta, sf->dat, sf->dax, sf->day, sf->dan, sf->ux, sf->uy, sf->un, sf->T, sf->P, sf->E,
+                                  sf->pixx, sf->pixy, sf->pixn, sf->piyy, sf->piyn, sf->bulkPi};
+  const bool need[n_raw] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
+                            (bool)fl->include_shear_deltaf, (bool)fl->include_shear_deltaf, (bool)fl->include_shear_deltaf,
+                            (bool)fl->include_shear_deltaf, (bool)fl->include_shear_deltaf, (bool)fl->include_bulk_deltaf};
+  for (int a = 0; a < n_raw; a++)
+    if (need[a] && !raw_src[a] && n_cells > 0) return fail(IS3D_ERR_ARGUMENT, "a required surface array is NULL");
+
+  const size_t rec_Y = (size_t)L.n_ytiles * L.n_cells_pad * L.nst * kRec * 8;
+  const size_t rec_P = (size_t)L.n_ptiles * L.n_cells_pad * L.npt * kRec * 8;
+  const size_t rec_S = (size_t)L.n_cells_pad * kScal * 8;
+  CU_CHECK(g_ws.small.reserve(ar.host.size() + 256));
+  CU_CHECK(g_ws.Y.reserve(rec_Y + 256));
+  CU_CHECK(g_ws.P.reserve(rec_P + 256));
+  CU_CHECK(g_ws.S.reserve(rec_S + 256));
+  CU_CHECK(g_ws.partial.reserve((size_t)n_chunks * n_bins * 8 + 256));
+  CU_CHECK(g_ws.counters.reserve(256));
+  const size_t cell_stride = ((size_t)n_cells * 8 + 255) & ~(size_t)255;
+  if (opt.memory == 0) {
+    CU_CHECK(g_ws.raw.reserve(cell_stride * n_raw + 256));
+    CU_CHECK(g_ws.dN.reserve((size_t)n_bins * 8 + 256));
+  }
+
+  cudaEvent_t *ev = g_ws.ev;
+  CU_CHECK(cudaEventRecord(ev[0], st));
+  // ---- host -> device
+  unsigned char *small_d = g_ws.small.as<unsigned char>();
+  CU_CHECK(cudaMemcpyAsync(small_d, ar.host.data(), ar.host.size(), cudaMemcpyHostToDevice, st));
+  RawCells rc; memset(&rc, 0, sizeof(rc));
+  rc.n = n_cells;
+  const double *raw_dev[n_raw];
+  for (int a = 0; a < n_raw; a++) {
+    raw_dev[a] = nullptr;
+    if (!need[a] || n_cells == 0) continue;
+    if (opt.memory == 0) {
+      double *dst = reinterpret_cast<double *>(g_ws.raw.as<unsigned char>() + cell_stride * a);
+      CU_CHECK(cudaMemcpyAsync(dst, raw_src[a], (size_t)n_cells * 8, cudaMemcpyHostToDevice, st));
+      raw_dev[a] = dst;
+    } else raw_dev[a] = raw_src[a];
+  }
+  rc.tau = raw_dev[0]; rc.eta = raw_dev[1]; rc.dat = raw_dev[2]; rc.dax = raw_dev[3]; rc.day = raw_dev[4]; rc.dan = raw_dev[5];
+  rc.ux = raw_dev[6]; rc.uy = raw_dev[7]; rc.un = raw_dev[8]; rc.T = raw_dev[9]; rc.P = raw_dev[10]; rc.E = raw_dev[11];
+  rc.pixx = raw_dev[12]; rc.pixy = raw_dev[13]; rc.pixn = raw_dev[14]; rc.piyy = raw_dev[15]; rc.piyn = raw_dev[16]; rc.bulkPi = raw_dev[17];
+  double *dN_dev = (opt.memory == 0) ? g_ws.dN.as<double>() : dN_out;
+  if (opt.memory == 0) CU_CHECK(cudaMemsetAsync(dN_dev, 0, (size_t)n_bins * 8, st));
+  CU_CHECK(cudaMemsetAsync(g_ws.counters.p, 0, sizeof(PrepCounters), st));
+  CU_CHECK(cudaEventRecord(ev[1], st));
+
+  // ---- prepare
+  auto dptr = [&](size_t off) { return reinterpret_cast<const double *>(small_d + off); };
+  PrepTables tab; memset(&tab, 0, sizeof(tab));
+  auto mk = [&](const SplineOff &o) { Spline s; s.x = dptr(o_T); s.y = dptr(o.y); s.c = dptr(o.c); s.n = df->n_T; return s; };
+  tab.c0 = mk(s_c0); tab.c2 = mk(s_c2); tab.F = mk(s_F); tab.betabulk = mk(s_bb); tab.betapi = mk(s_bp);
+  tab.cosphi = dptr(o_cos); tab.sinphi = dptr(o_sin); tab.slot_y = dptr(o_sloty); tab.slot_w = dim2 ? dptr(o_slotw) : nullptr;
+  if (fl->df_mode == 1 && (!df->c0 || !df->c2)) return fail(IS3D_ERR_ARGUMENT, "df_mode 1 needs the c0 and c2 tables");
+  if (fl->df_mode == 2 && (!df->F || !df->betabulk || !df->betapi)) return fail(IS3D_ERR_ARGUMENT, "df_mode 2 needs the F, betabulk and betapi tables");
+  CU_CHECK(launch_prepare_vh(*fl, rc, tab, L, g_ws.Y.as<double>(), g_ws.P.as<double>(), g_ws.S.as<double>(),
+                             g_ws.counters.as<PrepCounters>(), st));
+  stt.gpu_launches++;
+  CU_CHECK(cudaEventRecord(ev[2], st));
+
+  // ---- hot kernel
+  HotParams hp; memset(&hp, 0, sizeof(hp));
+  hp.L = L; hp.Y = g_ws.Y.as<double>(); hp.P = g_ws.P.as<double>(); hp.S = g_ws.S.as<double>();
+  hp.mass = dptr(o_mass); hp.sign = dptr(o_sign); hp.degeneracy = dptr(o_deg); hp.pT = dptr(o_pT);
+  hp.partial = g_ws.partial.as<double>();
+  hp.n_chunks = n_chunks; hp.n_groupblocks = n_groupblocks; hp.n_warps = n_warps;
+  hp.regulate_thr = fl->regulate_deltaf ? 0x3ff00000 : 0x7ff80000;
+  hp.outflow_thr = fl->outflow ? 0LL : (long long)0x8000000000000000ULL;
+  hp.prefactor = pow(2.0 * M_PI * 0.197327053, -3);                    // smooth_kernels.cpp:36
+  CU_CHECK(launch_hot_vh(*fl, hp, variant, st, nullptr));
+  stt.gpu_launches++;
+  CU_CHECK(cudaEventRecord(ev[3], st));
+
+  // ---- reduce chunks, add into the result
+  CU_CHECK(launch_reduce(hp.partial, n_chunks, n_bins, dN_dev, st));
+  stt.gpu_launches++;
+  CU_CHECK(cudaEventRecord(ev[4], st));
+
+  // ---- device -> host
+  PrepCounters cnt; memset(&cnt, 0, sizeof(cnt));
+  std::vector<double> host_dN;
+  if (opt.memory == 0) {
+    host_dN.resize((size_t)n_bins);
+    CU_CHECK(cudaMemcpyAsync(host_dN.data(), dN_dev, (size_t)n_bins * 8, cudaMemcpyDeviceToHost, st));
+  }
+  CU_CHECK(cudaMemcpyAsync(&cnt, g_ws.counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+  CU_CHECK(cudaEventRecord(ev[5], st));
+  CU_CHECK(cudaEventSynchronize(ev[5]));
+  if (opt.memory == 0)
+    for (int64_t i = 0; i < n_bins; i++) dN_out[i] += host_dN[(size_t)i];
+
+  float ms;
+  cudaEventElapsedTime(&ms, ev[0], ev[1]); stt.h2d_ms = ms;
+  cudaEventElapsedTime(&ms, ev[1], ev[2]); stt.prepare_ms = ms;
+  cudaEventElapsedTime(&ms, ev[2], ev[3]); stt.kernel_ms = ms;
+  cudaEventElapsedTime(&ms, ev[3], ev[4]); stt.reduce_ms = ms;
+  cudaEventElapsedTime(&ms, ev[4], ev[5]); stt.d2h_ms = ms;
+  cudaEventElapsedTime(&ms, ev[0], ev[5]); stt.total_ms = ms;
+  stt.cells_skipped_udsigma = (int64_t)cnt.skipped;
+  stt.cells_feqmod_breakdown = (int64_t)cnt.breakdown;
+  stt.evaluations = n_cells * (int64_t)sp->n * gr->n_pT * gr->n_phi * (dim2 ? (int64_t)gr->n_eta : (int64_t)gr->n_y);
+  stt.n_chunks = n_chunks; stt.tile_variant = variant;
+  if (stats) *stats = stt;
+  if (cnt.range_error) return fail(IS3D_ERR_TABLE_RANGE, "cell temperature outside the delta-f coefficient table");
+  (void)gla;
+  return IS3D_OK;
+}
+
+}  // extern "C"

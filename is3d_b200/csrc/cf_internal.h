@@ -1,0 +1,68 @@
+// cf_internal.h -- structures shared by the prepare kernels, the hot kernels and the C-ABI glue.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/is3d_b200.h"
+
+namespace is3d {
+
+constexpr int kRec = 6;          // doubles per slot / phi record
+constexpr int kScal = 4;         // doubles per per-cell scalar record
+constexpr int kMaxWarps = 4;     // warps per hot-kernel block (each warp = 32 consecutive (species, pT) pairs)
+constexpr int kStages = 4;       // TMA pipeline depth
+
+// Device-side view of the raw surface (GeV/fm units), NULL where switched off
+struct RawCells {
+  int64_t n;
+  const double *tau, *eta, *dat, *dax, *day, *dan, *ux, *uy, *un, *T, *P, *E;
+  const double *pixx, *pixy, *pixn, *piyy, *piyn, *bulkPi;
+  const double *pitt, *pitx, *pity, *pitn, *pinn, *Wx, *Wy, *Lambda, *aL, *c0, *c1, *c2, *c3, *c4;
+};
+
+// natural cubic spline table on the device: knots x[n], values y[n], second-derivative coefficients c[n]
+struct Spline { const double *x, *y, *c; int n; };
+
+struct PrepTables {
+  Spline c0, c2, F, betabulk, betapi, lam2, z;
+  double bulkPi_over_Peq_max;
+  const double *cosphi, *sinphi;        // [n_phi]
+  const double *slot_y;                 // 3+1D: y values [n_y];  2+1D: eta values [n_eta]
+  const double *slot_w;                 // 2+1D: eta weights [n_eta]; 3+1D: NULL
+  const double *gla_root1, *gla_w1, *gla_root2, *gla_w2; int gla_n;   // feqmod
+};
+
+// Geometry of the tiled record arrays
+//   Y[n_ytiles][n_cells_pad][nst][kRec]   slot records (nst = slots per tile)
+//   P[n_ptiles][n_cells_pad][npt][kRec]   phi records
+//   S[n_cells_pad][kScal]                 per-cell scalars
+struct Layout {
+  int n_species, n_pT, n_phi, n_y_out;   // output array dims (n_y_out = y table length)
+  int n_slots;                           // rapidity slots per cell: n_y (3+1D) or n_eta (2+1D)
+  int dim2;
+  int nst, n_ytiles, npt, n_ptiles;
+  int ct;                                // cells per TMA tile
+  int64_t n_cells, n_cells_pad, n_tiles;
+};
+
+struct PrepCounters { unsigned long long skipped, breakdown, range_error; };
+
+struct HotParams {
+  Layout L;
+  const double *Y, *P, *S;
+  const double *mass, *sign, *degeneracy, *pT;    // species / pT tables on device
+  double *partial;                                 // [n_chunks][n_bins]
+  int n_chunks, n_groupblocks, n_warps;
+  long long outflow_thr;                           // bit pattern threshold of the p.dsigma > 0 test
+  double prefactor;
+  int regulate_thr;                                // high-word threshold of |df| >= 1, see clamp_unit()
+};
+
+// launchers (cf_prepare.cu / cf_kernels.cu)
+cudaError_t launch_prepare_vh(const is3d_flags &fl, const RawCells &cells, const PrepTables &tab, const Layout &L,
+                              double *Y, double *P, double *S, PrepCounters *counters, cudaStream_t st);
+cudaError_t launch_hot_vh(const is3d_flags &fl, const HotParams &hp, int variant, cudaStream_t st, size_t *smem_out);
+cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, double *out, cudaStream_t st);
+cudaError_t launch_fp64_peak(double *sink, int iters, cudaStream_t st, int *blocks, int *threads, long long *dfma_per_thread);
+void hot_variant_shape(int variant, int dim2, int *nyt, int *npt, int *ct);
+
+}  // namespace is3d
