@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- smooth Cooper-Frye spectra throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg4ce]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one pass of the hot path (prepare + spectra kernel + chunk reduction [+ all-reduce]) over the whole synthetic
+surface.  The default workload is BASELINE.json configs[2]: 1 000 000-cell 3+1D viscous surface, full PDG (305 species,
+hrg_eos = 1), 14-moment delta-f, 32 x 24 x 21 momentum bins = 4.92e12 evaluations per step.  For N > 1 the SAME surface is
+sharded by cell over the ranks (strong scaling, as north_star defines it) and the 39 MB spectra array is all-reduced (NCCL).
+
+value  : evaluations/s with the surface already resident in HBM (CUDA events around K steps, max over ranks).
+e2e    : the same metric through the C ABI with HOST buffers: H2D of the (pinned) surface arrays and D2H of the spectra
+         inside the timed region.
+roofline: FP64 pipe.  achieved = 85 flop/evaluation (the reference's inner loop as written) x evaluations per
+         launch / mean spectra-kernel time (CUDA events inside the C ABI, on the launch stream); peak = FP64 DFMA roof
+         measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry).  HBM traffic is reported to show it is not the bound.
+cpu_baseline: the UNMODIFIED reference (oracle/_ref/is3d_ref_omp, -O3 -fopenmp, all host cores) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_EVAL = {1: 85.0, 2: 87.0, 3: 140.0, 4: 140.0}
+IDEAL_FLOPS = 29.0
+
+WORKLOADS = {
+    # name: (cells, dimension, df_mode, chosen, viscous, description)
+    "cfg3": (1_000_000, 3, 1, "chosen_urqmd", True, "cfg3: 1M-cell 3+1D viscous surface, full PDG (305 species), 14-moment df"),
+    "cfg4ce": (1_000_000, 3, 2, "chosen_urqmd", True, "cfg4: 1M-cell 3+1D viscous surface, full PDG, Chapman-Enskog df"),
+    "cfg4mike": (1_000_000, 3, 3, "chosen_urqmd", True, "cfg4: 1M-cell 3+1D viscous surface, full PDG, feqmod (Mike)"),
+    "cfg4jonah": (1_000_000, 3, 4, "chosen_urqmd", True, "cfg4: 1M-cell 3+1D viscous surface, full PDG, feqmod (Jonah)"),
+    "cfg2": (100_000, 2, 1, "chosen_pikp", False, "cfg2: 100k-cell boost-invariant surface, pi/K/p, ideal f_eq, 241-point eta quadrature"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--cells", type=int, default=0, help="override the cell count (development only; reported in config)")
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.path = tempfile.mktemp(prefix="is3d_clk_")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [[c.strip() for c in l.split(",")] for l in open(self.path).read().strip().splitlines() if l.strip()]
+            sm = [float(r[0]) for r in rows]
+            busy = [s for s, r in zip(sm, rows) if float(r[2]) > 250.0] or sm      # samples under load
+            out["sm_mhz"] = statistics.median(busy)
+            out["sm_max_mhz"] = float(rows[0][1])
+            out["power_w_max"] = max(float(r[2]) for r in rows)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            out["reasons"] = [n for j, n in enumerate(names) if any(r[3 + j].lower().startswith("active") for r in rows)]
+            out["samples"] = len(rows)
+        except Exception as e:          # never let monitoring break the measurement
+            out["error"] = str(e)
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ reference arm / CPU baseline
+def reference_sample(workload, cells=4000, n_species=4, threads=None, repeats=1):
+    """Time the unmodified reference (OpenMP build, all host cores) on a bounded sample of the workload.
+
+    Returns dict(value evals/s, cores, kind, sample, seconds list).  Falls back to the C oracle ("port") if the reference
+    binary is not present in oracle/_ref."""
+    from is3d_b200 import synthetic, tables, workdir
+    from oracle import cf_oracle as cfo
+    n_full, dim, dfm, chosen, viscous, desc = WORKLOADS[workload]
+    fx = tables.load_fixture()
+    threads = threads or os.cpu_count() or 1
+    if dim == 2:
+        cells = max(cells // 20, 50)
+    cols = synthetic.surface_vh(cells, synthetic.SEEDS["cfg3" if dim == 3 else "cfg2"], three_d=(dim == 3), viscous=viscous)
+    ids = list(fx[chosen][:n_species])
+    sp = tables.species(fx, 1, ids); g = tables.grid(fx)
+    evals = cells * len(ids) * len(g["pT"]) * len(g["phi"]) * (len(g["y"]) if dim == 3 else len(g["eta"]))
+    secs = []
+    exe = cfo.ref_binary(omp=True)
+    if exe is not None:
+        wd = tempfile.mkdtemp(prefix="is3d_ref_")
+        try:
+            workdir.materialize(wd, surface_columns=cols, chosen=ids, fixture=fx, operation=1, mode=1, hrg_eos=1, dimension=dim,
+                                df_mode=dfm, include_bulk_deltaf=int(viscous), include_shear_deltaf=int(viscous))
+            for _ in range(repeats):
+                _, info = cfo.run_reference(wd, what="kernel", omp=True, threads=threads)
+                secs.append(info["seconds"])
+        finally:
+            shutil.rmtree(wd, ignore_errors=True)
+        kind = "reference"
+        note = "unmodified reference src/cpp, g++ -O3 -fopenmp (CMakeLists.txt:11), OMP_NUM_THREADS=%d, kernel call only" % threads
+        if dim == 3:
+            note += "; timing only: the reference's 3+1D OpenMP results are wrong (data race, SURVEY R3)"
+    else:
+        cells_soa = synthetic.columns_to_cells(cols, 1)
+        tab = tables.df_tables(fx, 1); gla = tables.laguerre(fx)
+        fl = tables.flags(df_mode=dfm, dimension=dim, include_bulk=int(viscous), include_shear=int(viscous))
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+        for _ in range(repeats):
+            t0 = time.perf_counter(); cfo.smooth(fl, cells_soa, sp, g, tab, gla); secs.append(time.perf_counter() - t0)
+        kind = "port"
+        note = "oracle/cf_oracle.c (OpenMP over species, %d threads)" % threads
+    best = min(secs)
+    return dict(value=evals / best, unit="evaluations/s", cores=threads, kind=kind,
+                sample="%d-cell prefix x first %d species of %s (%d evaluations); %s" % (cells, len(ids), chosen, evals, note),
+                seconds=secs, evaluations=evals)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_full, dim, dfm, chosen, viscous, desc = WORKLOADS[args.workload]
+    total = args.steps + args.warmup
+    t0 = time.perf_counter()
+    res = reference_sample(args.workload, repeats=total)
+    secs = res["seconds"][args.warmup:]
+    mean = sum(secs) / len(secs)
+    value = res["evaluations"] / mean
+    line = {
+        "impl": "reference", "metric": "Cooper-Frye cell*momentum*species evaluations/s", "value": value, "unit": "evaluations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "sample": res["sample"], "wall_s": time.perf_counter() - t0},
+        "cpu_baseline": {"value": value, "unit": "evaluations/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
+        "e2e": {"value": value, "unit": "evaluations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from is3d_b200 import api, distributed, synthetic, tables
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 or args.gpus > 1:
+        if world != args.gpus:
+            raise SystemExit("--gpus %d needs torchrun with %d ranks (WORLD_SIZE=%d)" % (args.gpus, args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl")
+    api.init()
+
+    n_full, dim, dfm, chosen, viscous, desc = WORKLOADS[args.workload]
+    n_cells = args.cells or n_full
+    fx = tables.load_fixture()
+    sp = tables.species(fx, 1, chosen); g = tables.grid(fx); tab = tables.df_tables(fx, 1); gla = tables.laguerre(fx)
+    fl = tables.flags(df_mode=dfm, dimension=dim, include_bulk=int(viscous), include_shear=int(viscous))
+    cols = synthetic.surface_vh(n_cells, synthetic.SEEDS["cfg3" if dim == 3 else "cfg2"], three_d=(dim == 3), viscous=viscous)
+    cells = synthetic.columns_to_cells(cols, 1)
+    del cols
+    if dfm == 4:                                   # global lambda/z tables at the surface-average temperature, before sharding
+        pdg = tables.pdg_table(fx, 1)
+        avg = api.surface_averages(cells)
+        tab.update(api.jonah_tables(pdg["mass"], pdg["gspin"].astype(float), pdg["sign"].astype(float), avg[0], gla))
+    keys = ["tau", "eta", "dat", "dax", "day", "dan", "ux", "uy", "un", "T", "P", "E", "pixx", "pixy", "pixn", "piyy", "piyn", "bulkPi"]
+    lo, hi = distributed.shard_bounds(n_cells, rank, world)
+    # pinned host copies of this rank's shard (e2e leg) and device-resident copies (value leg)
+    host = {k: torch.from_numpy(np.ascontiguousarray(cells[k][lo:hi])).pin_memory() for k in keys}
+    host_np = {k: v.numpy() for k, v in host.items()}
+    dev = {k: v.cuda(non_blocking=True) for k, v in host.items()}
+    del cells
+    n_bins = len(sp["mass"]) * len(g["pT"]) * len(g["phi"]) * len(g["y"])
+    evals_step = n_cells * len(sp["mass"]) * len(g["pT"]) * len(g["phi"]) * (len(g["y"]) if dim == 3 else len(g["eta"]))
+    out = torch.zeros(n_bins, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        out.zero_()
+        _, st = api.smooth_spectra(fl, dev, sp, g, tab, gla, out=out, memory="device", tile_variant=args.variant)
+        if world > 1:
+            dist.all_reduce(out, op=dist.ReduceOp.SUM)
+        return st
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # roofline denominator, measured live on this GPU before the timed region
+    peak_burst, _ = api.measure_fp64_peak()
+    peak_sustained = api.measure_fp64_sustained(2.0)
+
+    for _ in range(args.warmup):
+        step_device()
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    kernel_ms, prepare_ms, reduce_ms, launches = [], [], [], 0
+    e0.record(stream)
+    for _ in range(args.steps):
+        st = step_device()
+        kernel_ms.append(st["kernel_ms"]); prepare_ms.append(st["prepare_ms"]); reduce_ms.append(st["reduce_ms"])
+        launches += st["gpu_launches"] + 1                     # + out.zero_() fill kernel
+    e1.record(stream)
+    sync_all()
+    clocks = sampler.stop() if sampler else None
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        k = torch.tensor([sum(kernel_ms) / len(kernel_ms)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(k, op=dist.ReduceOp.MAX)
+        kernel_mean = float(k.item())
+    else:
+        kernel_mean = sum(kernel_ms) / len(kernel_ms)
+    ms_step = ms_total / args.steps
+    value = evals_step / (ms_step * 1e-3)
+    checksum = float(out.sum().item())
+
+    # ---- end to end through the C ABI with host buffers
+    e2e = None
+    if not args.no_e2e:
+        host_out = np.zeros(n_bins)
+        pinned_out = torch.zeros(n_bins, dtype=torch.float64).pin_memory()
+
+        def step_host():
+            if world == 1:
+                host_out[:] = 0.0
+                api.smooth_spectra(fl, host_np, sp, g, tab, gla, out=host_out, tile_variant=args.variant)
+                return host_out
+            d = {k: v.cuda(non_blocking=True) for k, v in host.items()}       # H2D of this rank's shard, every step
+            out.zero_()
+            api.smooth_spectra(fl, d, sp, g, tab, gla, out=out, memory="device", tile_variant=args.variant)
+            dist.all_reduce(out, op=dist.ReduceOp.SUM)
+            pinned_out.copy_(out, non_blocking=False)                            # D2H of the reduced spectra
+            return pinned_out.numpy()
+
+        step_host()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = step_host()
+        sync_all()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": evals_step / (dt / args.steps), "unit": "evaluations/s",
+               "h2d_bytes_per_step": int(len(keys) * 8 * n_cells), "d2h_bytes_per_step": int(n_bins * 8 * world),
+               "checksum_rel_diff": abs(float(np.sum(res)) - checksum) / abs(checksum) if checksum else 0.0}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the spectra kernel) on rank 0's shard
+    W = (FLOPS_PER_EVAL[dfm] if viscous else IDEAL_FLOPS)
+    evals_launch = evals_step / world
+    achieved = W * evals_launch / (kernel_mean * 1e-3) * 1e-12
+    slots = len(g["y"]) if dim == 3 else len(g["eta"])
+    rec_bytes = (hi - lo) * (slots * 48 + len(g["phi"]) * 48 + 32)         # record arrays read once per block column
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_sustained, "unit": "TFLOP/s", "frac": achieved / peak_sustained,
+                "traffic": None, "flops_per_evaluation": W, "kernel_ms": kernel_mean, "kernel_share_of_step": kernel_mean / ms_step,
+                "peak_source": "measured live: dependency-free DFMA chains on all SMs, %.1f s sustained (burst %.2f TFLOP/s); "
+                               "MEASURED_PEAKS.json has no FP64 entry" % (2.0, peak_burst),
+                "hbm": {"record_bytes_per_launch": int(rec_bytes), "note": "records are re-read by every bin-tile column from L2/HBM; "
+                        "see profiles/ for dram__bytes of the ncu capture", "hbm_peak_gbs": _measured_hbm()}}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            r = reference_sample(args.workload)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:          # the baseline is a reported number, never a reason to lose the GPU measurement
+            cpu = {"value": None, "unit": "evaluations/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (e,)}
+
+    line = {
+        "metric": "Cooper-Frye cell*momentum*species evaluations/s", "value": value, "unit": "evaluations/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "cells": n_cells, "species": len(sp["mass"]), "momentum_bins": len(g["pT"]) * len(g["phi"]) * len(g["y"]),
+                   "evaluations_per_step": evals_step, "sharding": "cells split contiguously over %d rank(s), one all-reduce of %d doubles" % (world, n_bins),
+                   "l2": "inputs larger than L2: %.0f MB of raw cell arrays + %.0f MB of per-cell records per rank vs 126 MB L2"
+                         % (len(keys) * 8 * (hi - lo) / 1e6, rec_bytes / 1e6),
+                   "tile_variant": args.variant, "underflow_skip": "evaluations whose exp(u.p/T) overflows (f = 0 exactly in the reference) are skipped; they still count as evaluations",
+                   "spectra_checksum": checksum},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "fraction_of_fp64_peak": achieved / peak_sustained,
+        "timing": {"prepare_ms": sum(prepare_ms) / len(prepare_ms), "kernel_ms": kernel_mean, "reduce_ms": sum(reduce_ms) / len(reduce_ms)},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def _measured_hbm():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        return 6650.0          # fallback stated in B200_PROFILING.md
+
+
+if __name__ == "__main__":
+    main()

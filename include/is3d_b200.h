@@ -123,6 +123,20 @@ int is3d_b200_measure_fp64_sustained(double seconds, double *tflops);
  * results/dN_dy_*.dat with the reference's formats.  If dN_raw != NULL it receives the spectra (n_raw doubles max). */
 int is3d_b200_run_workdir(const char *workdir, double *dN_raw, int64_t n_raw, int32_t *mcid_out, int32_t n_mcid_max,
                           is3d_stats *stats);
+/* Host-side table builders for callers that drive is3d_b200_smooth_spectra() directly (no working directory):
+ *  - surface averages T, E, P, muB, nB weighted as in FO_data_reader::read_surf_VH (readindata.cpp:423-466), passed through
+ *    the reference's 15-significant-digit side file round trip (average_thermodynamic_quantities.dat);
+ *  - the Jonah lambda^2(Pi/P), z(Pi/P) tables of Deltaf_Data::compute_jonah_coefficients (deltafReader.cpp:222-297):
+ *    301 points each, built from the full particle list at temperature T_avg with the alpha = 2 Gauss-Laguerre nodes. */
+int is3d_b200_surface_averages(const is3d_surface *surface, double *out5);
+int is3d_b200_jonah_tables(int32_t n_particles, const double *mass, const double *degeneracy, const double *sign, double T_avg,
+                           int32_t n_points, const double *root2, const double *weight2,
+                           double *x301, double *lambda2_301, double *z301, double *bulkPi_over_Peq_max);
+/* Writers only: produce the results/ files of `workdir` from a spectra array in the reference layout. */
+int is3d_b200_write_results(const char *workdir, const double *dN, int64_t n);
+/* Host-layer inspection without GPU work: dumps what the readers derived (named double records) to out_path. */
+int is3d_b200_host_dump(const char *workdir, const char *out_path);
+const char *is3d_b200_host_error(void);
 
 #ifdef __cplusplus
 }

@@ -118,6 +118,30 @@ def measure_fp64_sustained(seconds=3.0):
     return t.value
 
 
+def surface_averages(cells):
+    """T, E, P, muB, nB surface averages after the reference's 15-digit text round trip (host arrays)."""
+    m = _Marshal(False)
+    sf = Surface(); sf.n_cells = len(cells["tau"])
+    for k in SURFACE_FIELDS:
+        if k in cells and cells[k] is not None:
+            setattr(sf, k, m.cells(cells[k]))
+    out = np.zeros(5)
+    _check(lib().is3d_b200_surface_averages(C.byref(sf), out.ctypes.data_as(_D)))
+    return out
+
+
+def jonah_tables(pdg_mass, pdg_degeneracy, pdg_sign, T_avg, laguerre):
+    """lambda^2(Pi/P), z(Pi/P) tables for df_mode 4 (host computation in the C++ layer)."""
+    m = _Marshal(False)
+    x = np.zeros(301); l2 = np.zeros(301); z = np.zeros(301); mx = C.c_double(0)
+    f = lib().is3d_b200_jonah_tables
+    f.argtypes = [C.c_int32, _D, _D, _D, C.c_double, C.c_int32, _D, _D, _D, _D, _D, C.POINTER(C.c_double)]
+    _check(f(len(pdg_mass), m.host(pdg_mass), m.host(pdg_degeneracy), m.host(pdg_sign), float(T_avg), len(laguerre["root2"]),
+             m.host(laguerre["root2"]), m.host(laguerre["weight2"]), x.ctypes.data_as(_D), l2.ctypes.data_as(_D),
+             z.ctypes.data_as(_D), C.byref(mx)))
+    return dict(jonah_x=x, jonah_lambda2=l2, jonah_z=z, bulkPi_over_Peq_max=mx.value)
+
+
 def _is_torch(x):
     return type(x).__module__.startswith("torch")
 

@@ -1,0 +1,363 @@
+// host_run.cpp -- the drop-in driver behind the iS3D file interface: is3d_b200_run_workdir().
+//
+// Call order follows IS3D::run_particlization(1) for operation = 1 (reference src/cpp/iS3D.cpp:73-191):
+// parameters -> surface (+ averages side file) -> particle list -> delta-f tables (+ Jonah tables) -> chosen species ->
+// momentum tables -> spectra (GPU, through the C ABI) -> result files.  Species bookkeeping mirrors the
+// EmissionFunctionArray constructor (emissionfunction.cpp:310-369, 1293-1307); the writers reproduce the text formats of
+// write_dN_pTdpTdphidy_toFile (:381-450), write_continuous_vn_toFile (:1053-1136) and write_dN_dy_toFile (:729-772),
+// including append mode and the requirement that results/ already exists.
+#include "../../include/is3d_b200.h"
+#include "host_io.h"
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <string>
+#include <vector>
+
+namespace is3d {
+
+static std::string g_host_error;
+
+struct Grids {
+  BlockTable pT, phi, y, eta;
+};
+
+static inline long long bin_index(int ipart, int npart, int ipT, int npT, int iphi, int nphi, int iy)
+{ return (long long)ipart + (long long)npart * ((long long)ipT + (long long)npT * ((long long)iphi + (long long)nphi * (long long)iy)); }
+
+static bool write_spectra_files(const std::string &wd, const std::vector<double> &dN, const std::vector<int> &mcid,
+                                const Grids &g, int dimension, std::string *err)
+{
+  const int npart = (int)mcid.size(), npT = (int)g.pT.rows, nphi = (int)g.phi.rows;
+  const int y_pts = (dimension == 2) ? 1 : (int)g.y.rows;
+  auto rapidity = [&](int iy) { return (dimension == 2) ? 0.0 : g.y.at(1, iy + 1); };
+  // one block per (species, y, phi): rows "y \t phi \t pT \t dN", blank line after each phi block
+  auto dump = [&](std::ostream &os, int ipart) {
+    for (int iy = 0; iy < y_pts; iy++)
+      for (int iphi = 0; iphi < nphi; iphi++) {
+        for (int ipT = 0; ipT < npT; ipT++)
+          os << std::scientific << std::setw(5) << std::setprecision(8) << rapidity(iy) << "\t" << g.phi.at(1, iphi + 1) << "\t"
+             << g.pT.at(1, ipT + 1) << "\t" << dN[(size_t)bin_index(ipart, npart, ipT, npT, iphi, nphi, iy)] << "\n";
+        os << "\n";
+      }
+  };
+  {
+    std::ofstream all((wd + "/results/dN_pTdpTdphidy.dat").c_str(), std::ios_base::app);
+    if (!all) { *err = "cannot open results/dN_pTdpTdphidy.dat (does results/ exist?)"; return false; }
+    for (int ipart = 0; ipart < npart; ipart++) dump(all, ipart);
+  }
+  for (int ipart = 0; ipart < npart; ipart++) {
+    char name[255];
+    std::snprintf(name, sizeof(name), "%s/results/dN_pTdpTdphidy_%d.dat", wd.c_str(), mcid[ipart]);
+    std::ofstream one(name, std::ios_base::app);
+    if (!one) { *err = std::string("cannot open ") + name; return false; }
+    one << "y" << "\t" << "phip" << "\t" << "pT" << "\t" << "dN_pTdpTdphidy" << "\n";
+    dump(one, ipart);
+  }
+
+  // continuous v_n(pT, y), n = 1..7: |sum_phi w e^{i n phi} dN| / sum_phi w dN
+  const int k_max = 7;
+  for (int ipart = 0; ipart < npart; ipart++) {
+    char name[255];
+    std::snprintf(name, sizeof(name), "%s/results/vn_continuous/vn_%d.dat", wd.c_str(), mcid[ipart]);
+    std::ofstream vf(name, std::ios_base::app);
+    if (!vf) { *err = std::string("cannot open ") + name; return false; }
+    for (int iy = 0; iy < y_pts; iy++) {
+      const double y = (dimension == 2) ? 0.0 : g.y.at(1, iy + 1);
+      for (int ipT = 0; ipT < npT; ipT++) {
+        double re[k_max], im[k_max], den = 0.0;
+        for (int k = 0; k < k_max; k++) { re[k] = 0.0; im[k] = 0.0; }
+        for (int iphi = 0; iphi < nphi; iphi++) {
+          const double phip = g.phi.at(1, iphi + 1), w = g.phi.at(2, iphi + 1);
+          const double v = dN[(size_t)bin_index(ipart, npart, ipT, npT, iphi, nphi, iy)];
+          for (int k = 0; k < k_max; k++) {
+            re[k] += std::cos(((double)k + 1.0) * phip) * w * v;
+            im[k] += std::sin(((double)k + 1.0) * phip) * w * v;
+          }
+          den += w * v;
+        }
+        vf << std::scientific << std::setw(5) << std::setprecision(8) << y << "\t" << g.pT.at(1, ipT + 1);
+        for (int k = 0; k < k_max; k++) {
+          double vn = std::abs(std::complex<double>(re[k], im[k])) / den;
+          if (den < 1.e-15) vn = 0.0;
+          vf << "\t" << vn;
+        }
+        vf << "\n";
+      }
+      vf << "\n";
+    }
+  }
+
+  // dN/dy = sum_phi sum_pT w_phi w_pT dN  (default float format, 8 significant digits)
+  for (int ipart = 0; ipart < npart; ipart++) {
+    char name[255];
+    std::snprintf(name, sizeof(name), "%s/results/dN_dy_%d.dat", wd.c_str(), mcid[ipart]);
+    std::ofstream yf(name, std::ios_base::app);
+    if (!yf) { *err = std::string("cannot open ") + name; return false; }
+    for (int iy = 0; iy < y_pts; iy++) {
+      double y = g.y.at(1, iy + 1);
+      if (dimension == 2) y = 0.0;
+      double dN_dy = 0.0;
+      for (int iphi = 0; iphi < nphi; iphi++) {
+        const double w_phi = g.phi.at(2, iphi + 1);
+        for (int ipT = 0; ipT < npT; ipT++)
+          dN_dy += w_phi * g.pT.at(2, ipT + 1) * dN[(size_t)bin_index(ipart, npart, ipT, npT, iphi, nphi, iy)];
+      }
+      yf << std::setw(5) << std::setprecision(8) << y << "\t" << dN_dy << "\n";
+    }
+  }
+  return true;
+}
+
+// everything the host layer derives from the input files
+struct Problem {
+  Params par;
+  is3d_flags fl;
+  int operation = 0, hrg_eos = 0, group_particles = 0;
+  SurfaceData sf;
+  std::vector<Particle> pdg;
+  DfTables dft;
+  Laguerre gla;
+  std::vector<double> mass, sign, degen, baryon;
+  std::vector<int> mcid;
+  Grids g;
+};
+
+static int load_problem(const std::string &wd, bool need_surface, Problem *p, std::string *err_out)
+{
+  std::string &err = *err_out;
+  Params &par = p->par;
+  if (!par.load(wd + "/iS3D_parameters.dat", &err)) return IS3D_ERR_IO;
+  // the reference constructor reads every key, sampler ones included, and a missing key is fatal
+  // (emissionfunction.cpp:170-222); keep that contract so that a file accepted here is accepted there
+  static const char *required[] = {"operation", "mode", "hrg_eos", "set_FO_temperature", "T_switch", "dimension", "df_mode",
+    "include_baryon", "include_bulk_deltaf", "include_shear_deltaf", "include_baryondiff_deltaf", "regulate_deltaf", "outflow",
+    "deta_min", "group_particles", "particle_diff_tolerance", "mass_pion0", "do_resonance_decays", "lightest_particle",
+    "oversample", "max_num_samples", "fast", "min_num_hadrons", "sampler_seed", "test_sampler", "pT_lower_cut", "pT_upper_cut",
+    "pT_bins", "y_cut", "y_bins", "eta_cut", "eta_bins", "tau_min", "tau_max", "tau_bins", "r_min", "r_max", "r_bins"};
+  for (const char *k : required) par.get(k, &err);
+  if (!err.empty()) return IS3D_ERR_IO;
+  p->operation = (int)par.get("operation", &err); p->hrg_eos = (int)par.get("hrg_eos", &err);
+  p->group_particles = (int)par.get("group_particles", &err);
+  is3d_flags &fl = p->fl; std::memset(&fl, 0, sizeof(fl));
+  fl.mode = (int)par.get("mode", &err); fl.df_mode = (int)par.get("df_mode", &err); fl.dimension = (int)par.get("dimension", &err);
+  fl.include_baryon = (int)par.get("include_baryon", &err);
+  fl.include_bulk_deltaf = (int)par.get("include_bulk_deltaf", &err);
+  fl.include_shear_deltaf = (int)par.get("include_shear_deltaf", &err);
+  fl.include_baryondiff_deltaf = (int)par.get("include_baryondiff_deltaf", &err);
+  fl.regulate_deltaf = (int)par.get("regulate_deltaf", &err);
+  fl.outflow = (int)par.get("outflow", &err);
+  fl.deta_min = par.get("deta_min", &err); fl.mass_pion0 = par.get("mass_pion0", &err);
+  if (p->operation != 1) { err = "this drop-in covers operation = 1 (smooth momentum spectra) only"; return IS3D_ERR_UNSUPPORTED; }
+  if ((int)par.get("do_resonance_decays", &err)) { err = "do_resonance_decays = 1 is outside the smooth-spectra path"; return IS3D_ERR_UNSUPPORTED; }
+
+  // ---- surface (+ averages side file)
+  if (need_surface) {
+    SurfaceFlags sfl{fl.mode, fl.dimension, fl.df_mode, fl.include_baryon, fl.include_baryondiff_deltaf};
+    if (!read_surface(wd, sfl, &p->sf, &err)) return IS3D_ERR_IO;
+  }
+  // ---- particle list, delta-f tables
+  if (!read_pdg(wd, p->hrg_eos, &p->pdg, &err)) return IS3D_ERR_IO;
+  if ((int)p->pdg.size() > 600) { err = "number of particles exceeds Maxparticle = 600"; return IS3D_ERR_IO; }
+  if (!read_df_tables(wd, p->hrg_eos, &p->dft, &err)) return IS3D_ERR_IO;
+  if (!read_laguerre(wd + "/tables/gla_roots_weights_32_points.txt", &p->gla, &err)) return IS3D_ERR_IO;
+  if (p->gla.alpha < 3) { err = "Gauss-Laguerre table needs alpha = 0..2"; return IS3D_ERR_IO; }
+  if (need_surface) {
+    if (fl.mode != 2 && fl.df_mode == 4) compute_jonah_tables(p->pdg, p->sf.avg[0], p->gla, &p->dft);
+    if (fl.mode == 2 && !fill_vah_coefficients(wd, &p->sf, &err)) return IS3D_ERR_IO;
+  }
+  // ---- chosen species in file order (first match in the particle list), optional mass bubble sort
+  BlockTable chosen;
+  if (!chosen.load(wd + "/PDG/chosen_particles.dat", &err)) return IS3D_ERR_IO;
+  const int npart = (int)chosen.rows;
+  std::vector<int> pick;
+  for (int m = 0; m < npart; m++) {
+    const int id = (int)chosen.at(1, m + 1);
+    int found = -1;
+    for (size_t n = 0; n < p->pdg.size(); n++) if (p->pdg[n].mcid == id) { found = (int)n; break; }
+    if (found < 0) { err = "chosen particle " + std::to_string(id) + " is not in the particle list (the reference leaves that slot uninitialised)"; return IS3D_ERR_IO; }
+    pick.push_back(found);
+  }
+  if (p->group_particles == 1)
+    for (int m = 0; m < npart; m++)
+      for (int n = 0; n < npart - m - 1; n++)
+        if (p->pdg[pick[n]].mass > p->pdg[pick[n + 1]].mass) std::swap(pick[n], pick[n + 1]);
+  p->mass.resize(npart); p->sign.resize(npart); p->degen.resize(npart); p->baryon.resize(npart); p->mcid.resize(npart);
+  for (int i = 0; i < npart; i++) {
+    const Particle &h = p->pdg[pick[i]];
+    p->mass[i] = h.mass; p->sign[i] = h.sign; p->degen[i] = h.gspin; p->baryon[i] = h.baryon; p->mcid[i] = (int)h.mcid;
+  }
+  // ---- momentum tables (iS3D.cpp:161-167)
+  Grids &g = p->g;
+  if (!g.pT.load(wd + "/tables/pT_gauss_legendre_table.dat", &err) || !g.phi.load(wd + "/tables/phi_gauss_legendre_table.dat", &err) ||
+      !g.y.load(wd + "/tables/y_trapezoid_table_21pt.dat", &err) || !g.eta.load(wd + "/tables/eta/eta_trapezoid_table_241pt.dat", &err))
+    return IS3D_ERR_IO;
+  if (g.pT.cols.size() < 2 || g.phi.cols.size() < 2 || g.eta.cols.size() < 2) { err = "momentum tables need a weight column"; return IS3D_ERR_IO; }
+  return IS3D_OK;
+}
+
+}  // namespace is3d
+
+using namespace is3d;
+
+extern "C" int is3d_b200_run_workdir(const char *workdir, double *dN_raw, int64_t n_raw, int32_t *mcid_out, int32_t n_mcid_max,
+                                     is3d_stats *stats)
+{
+  const std::string wd = (workdir && *workdir) ? workdir : ".";
+  std::string err;
+  auto fail = [&](int code) { g_host_error = err; std::fprintf(stderr, "is3d_b200: %s\n", err.c_str()); return code; };
+  Problem P;
+  int rc = load_problem(wd, true, &P, &err);
+  if (rc != IS3D_OK) return fail(rc);
+  const SurfaceData &sf = P.sf; const Grids &g = P.g; const DfTables &dft = P.dft; const Laguerre &gla = P.gla;
+  const int npart = (int)P.mcid.size(), mode = P.fl.mode;
+
+  // ---- spectra on the GPU
+  is3d_surface s; std::memset(&s, 0, sizeof(s));
+  s.n_cells = sf.n;
+  s.tau = sf.tau.data(); s.eta = sf.eta.data(); s.dat = sf.dat.data(); s.dax = sf.dax.data(); s.day = sf.day.data(); s.dan = sf.dan.data();
+  s.ux = sf.ux.data(); s.uy = sf.uy.data(); s.un = sf.un.data(); s.T = sf.T.data(); s.P = sf.P.data(); s.E = sf.E.data();
+  s.pixx = sf.pixx.data(); s.pixy = sf.pixy.data(); s.pixn = sf.pixn.data(); s.piyy = sf.piyy.data(); s.piyn = sf.piyn.data();
+  s.bulkPi = sf.bulkPi.data(); s.muB = sf.muB.data(); s.nB = sf.nB.data(); s.Vx = sf.Vx.data(); s.Vy = sf.Vy.data(); s.Vn = sf.Vn.data();
+  if (mode == 2) {
+    s.pitt = sf.pitt.data(); s.pitx = sf.pitx.data(); s.pity = sf.pity.data(); s.pitn = sf.pitn.data(); s.pinn = sf.pinn.data();
+    s.Wx = sf.Wx.data(); s.Wy = sf.Wy.data(); s.Lambda = sf.Lambda.data(); s.aL = sf.aL.data();
+    s.c0 = sf.c0.data(); s.c1 = sf.c1.data(); s.c2 = sf.c2.data(); s.c3 = sf.c3.data(); s.c4 = sf.c4.data();
+  }
+  is3d_species sp{npart, P.mass.data(), P.sign.data(), P.degen.data(), P.baryon.data()};
+  is3d_grid gr{(int32_t)g.pT.rows, (int32_t)g.phi.rows, (int32_t)g.y.rows, (int32_t)g.eta.rows,
+               g.pT.cols[0].data(), g.phi.cols[0].data(), g.y.cols[0].data(), g.eta.cols[0].data(), g.eta.cols[1].data()};
+  is3d_df_tables dt; std::memset(&dt, 0, sizeof(dt));
+  dt.n_T = dft.n_T; dt.T = dft.T.data(); dt.c0 = dft.c0.data(); dt.c1 = dft.c1.data(); dt.c2 = dft.c2.data(); dt.c3 = dft.c3.data();
+  dt.c4 = dft.c4.data(); dt.F = dft.F.data(); dt.G = dft.G.data(); dt.betabulk = dft.betabulk.data(); dt.betaV = dft.betaV.data();
+  dt.betapi = dft.betapi.data();
+  if (!dft.jonah_x.empty()) {
+    dt.n_jonah = (int32_t)dft.jonah_x.size(); dt.jonah_x = dft.jonah_x.data(); dt.jonah_lambda2 = dft.jonah_lambda2.data();
+    dt.jonah_z = dft.jonah_z.data(); dt.bulkPi_over_Peq_max = dft.bulkPi_over_Peq_max;
+  }
+  is3d_laguerre la{gla.points, gla.root[1].data(), gla.weight[1].data(), gla.root[2].data(), gla.weight[2].data()};
+
+  const size_t n_bins = (size_t)npart * g.pT.rows * g.phi.rows * g.y.rows;
+  std::vector<double> dN(n_bins, 0.0);
+  is3d_stats st; std::memset(&st, 0, sizeof(st));
+  rc = is3d_b200_smooth_spectra(&P.fl, &s, &sp, &gr, &dt, &la, nullptr, dN.data(), &st);
+  if (stats) *stats = st;
+  if (rc != IS3D_OK) { err = std::string("spectra kernel failed: ") + is3d_b200_last_error(); return fail(rc); }
+  if (P.fl.df_mode == 3 || P.fl.df_mode == 4)
+    std::cout << std::setw(5) << std::setprecision(4) << "\nfeqmod breaks down for " << st.cells_feqmod_breakdown << " cells\n" << std::endl;
+
+  if (dN_raw) std::memcpy(dN_raw, dN.data(), sizeof(double) * (size_t)std::min<int64_t>(n_raw, (int64_t)n_bins));
+  if (mcid_out) for (int i = 0; i < npart && i < n_mcid_max; i++) mcid_out[i] = P.mcid[i];
+  if (!write_spectra_files(wd, dN, P.mcid, g, P.fl.dimension, &err)) return fail(IS3D_ERR_IO);
+  return IS3D_OK;
+}
+
+// Writers only: takes a spectra array (reference layout) and produces the results/ files for `workdir`.
+extern "C" int is3d_b200_write_results(const char *workdir, const double *dN, int64_t n)
+{
+  const std::string wd = (workdir && *workdir) ? workdir : ".";
+  std::string err;
+  Problem P;
+  int rc = load_problem(wd, false, &P, &err);
+  if (rc != IS3D_OK) { g_host_error = err; return rc; }
+  const size_t n_bins = (size_t)P.mcid.size() * P.g.pT.rows * P.g.phi.rows * P.g.y.rows;
+  if (!dN || (size_t)n != n_bins) { g_host_error = "spectra array has the wrong length"; return IS3D_ERR_ARGUMENT; }
+  std::vector<double> v(dN, dN + n);
+  if (!write_spectra_files(wd, v, P.mcid, P.g, P.fl.dimension, &err)) { g_host_error = err; return IS3D_ERR_IO; }
+  return IS3D_OK;
+}
+
+// Host-layer inspection (no GPU work): parses every input file of `workdir` and writes what it derived -- species
+// arrays, surface SoA, coefficient tables -- as named records [int32 name_len][name][int64 n][n doubles] to `out_path`.
+extern "C" int is3d_b200_host_dump(const char *workdir, const char *out_path)
+{
+  const std::string wd = (workdir && *workdir) ? workdir : ".";
+  std::string err;
+  Problem P;
+  int rc = load_problem(wd, true, &P, &err);
+  if (rc != IS3D_OK) { g_host_error = err; return rc; }
+  FILE *f = std::fopen(out_path, "wb");
+  if (!f) { g_host_error = "cannot write dump"; return IS3D_ERR_IO; }
+  auto put = [&](const char *name, const std::vector<double> &v) {
+    int32_t len = (int32_t)std::strlen(name); int64_t n = (int64_t)v.size();
+    std::fwrite(&len, 4, 1, f); std::fwrite(name, 1, len, f); std::fwrite(&n, 8, 1, f);
+    if (n) std::fwrite(v.data(), 8, (size_t)n, f);
+  };
+  std::vector<double> tmp;
+  tmp.assign(P.mcid.begin(), P.mcid.end()); put("mcid", tmp);
+  put("mass", P.mass); put("sign", P.sign); put("degeneracy", P.degen); put("baryon", P.baryon);
+  tmp.clear(); for (auto &h : P.pdg) tmp.push_back((double)h.mcid); put("pdg_mcid", tmp);
+  tmp.clear(); for (auto &h : P.pdg) tmp.push_back(h.mass); put("pdg_mass", tmp);
+  tmp.clear(); for (auto &h : P.pdg) tmp.push_back(h.gspin); put("pdg_gspin", tmp);
+  tmp.clear(); for (auto &h : P.pdg) tmp.push_back(h.sign); put("pdg_sign", tmp);
+  tmp.clear(); for (auto &h : P.pdg) tmp.push_back(h.baryon); put("pdg_baryon", tmp);
+  const SurfaceData &s = P.sf;
+  put("tau", s.tau); put("eta", s.eta); put("dat", s.dat); put("dax", s.dax); put("day", s.day); put("dan", s.dan);
+  put("ux", s.ux); put("uy", s.uy); put("un", s.un); put("E", s.E); put("T", s.T); put("P", s.P);
+  put("pixx", s.pixx); put("pixy", s.pixy); put("pixn", s.pixn); put("piyy", s.piyy); put("piyn", s.piyn); put("bulkPi", s.bulkPi);
+  put("pitt", s.pitt); put("pitx", s.pitx); put("pity", s.pity); put("pitn", s.pitn); put("pinn", s.pinn);
+  put("Wx", s.Wx); put("Wy", s.Wy); put("Lambda", s.Lambda); put("aL", s.aL);
+  put("c0", s.c0); put("c1", s.c1); put("c2", s.c2); put("c3", s.c3); put("c4", s.c4);
+  tmp.assign(s.avg, s.avg + 5); put("avg", tmp);
+  put("df_T", P.dft.T); put("df_c0", P.dft.c0); put("df_c2", P.dft.c2); put("df_F", P.dft.F); put("df_betabulk", P.dft.betabulk);
+  put("df_betapi", P.dft.betapi); put("jonah_x", P.dft.jonah_x); put("jonah_lambda2", P.dft.jonah_lambda2); put("jonah_z", P.dft.jonah_z);
+  tmp.assign(1, P.dft.bulkPi_over_Peq_max); put("jonah_max", tmp);
+  put("pT", P.g.pT.cols[0]); put("phi", P.g.phi.cols[0]); put("y", P.g.y.cols[0]); put("eta_tab", P.g.eta.cols[0]); put("eta_weight", P.g.eta.cols[1]);
+  put("gla_root1", P.gla.root[1]); put("gla_weight2", P.gla.weight[2]);
+  tmp = {(double)P.fl.mode, (double)P.fl.df_mode, (double)P.fl.dimension, (double)P.fl.include_baryon, (double)P.fl.include_bulk_deltaf,
+         (double)P.fl.include_shear_deltaf, (double)P.fl.include_baryondiff_deltaf, (double)P.fl.regulate_deltaf, (double)P.fl.outflow,
+         P.fl.deta_min, P.fl.mass_pion0};
+  put("flags", tmp);
+  std::fclose(f);
+  return IS3D_OK;
+}
+
+extern "C" int is3d_b200_surface_averages(const is3d_surface *sf, double *out5)
+{
+  if (!sf || !out5 || sf->n_cells <= 0) return IS3D_ERR_ARGUMENT;
+  double Tavg = 0, Eavg = 0, Pavg = 0, muBavg = 0, nBavg = 0, volume = 0;
+  for (int64_t i = 0; i < sf->n_cells; i++) {
+    const double tau = sf->tau[i], ux = sf->ux[i], uy = sf->uy[i], un = sf->un[i];
+    const double ut = std::sqrt(1.0 + ux * ux + uy * uy + tau * tau * un * un);
+    const double dat = sf->dat[i], dax = sf->dax[i], day = sf->day[i], dan = sf->dan[i];
+    const double udsigma = ut * dat + ux * dax + uy * day + un * dan;
+    const double dsds = dat * dat - dax * dax - day * day - dan * dan / (tau * tau);
+    const double mag = std::fabs(udsigma) + std::sqrt(std::fabs(udsigma * udsigma - dsds));
+    const double muB = sf->muB ? sf->muB[i] : 0.0, nB = sf->nB ? sf->nB[i] : 0.0;
+    volume += mag;
+    Eavg += (sf->E[i] * mag); Tavg += (sf->T[i] * mag); Pavg += (sf->P[i] * mag); muBavg += (muB * mag); nBavg += (nB * mag);
+  }
+  const double v[5] = {Tavg / volume, Eavg / volume, Pavg / volume, muBavg / volume, nBavg / volume};
+  for (int k = 0; k < 5; k++) {                  // the reference writes these with 15 digits and reads them back
+    char buf[64];
+    std::snprintf(buf, sizeof(buf), "%.15g", v[k]);
+    out5[k] = std::strtod(buf, nullptr);
+  }
+  return IS3D_OK;
+}
+
+extern "C" int is3d_b200_jonah_tables(int32_t n_particles, const double *mass, const double *degeneracy, const double *sign, double T_avg,
+                                      int32_t n_points, const double *root2, const double *weight2,
+                                      double *x301, double *lambda2_301, double *z301, double *mx)
+{
+  if (n_particles <= 0 || !mass || !degeneracy || !sign || n_points <= 0 || !root2 || !weight2 || !x301 || !lambda2_301 || !z301)
+    return IS3D_ERR_ARGUMENT;
+  std::vector<Particle> pdg((size_t)n_particles);
+  for (int i = 0; i < n_particles; i++) { pdg[i].mass = mass[i]; pdg[i].gspin = (int)degeneracy[i]; pdg[i].sign = (int)sign[i]; }
+  Laguerre gla; gla.alpha = 3; gla.points = n_points;
+  gla.root.assign(3, std::vector<double>(root2, root2 + n_points)); gla.weight.assign(3, std::vector<double>(weight2, weight2 + n_points));
+  DfTables t;
+  compute_jonah_tables(pdg, T_avg, gla, &t);
+  std::memcpy(x301, t.jonah_x.data(), 301 * sizeof(double));
+  std::memcpy(lambda2_301, t.jonah_lambda2.data(), 301 * sizeof(double));
+  std::memcpy(z301, t.jonah_z.data(), 301 * sizeof(double));
+  if (mx) *mx = t.bulkPi_over_Peq_max;
+  return IS3D_OK;
+}
+
+extern "C" const char *is3d_b200_host_error(void) { return g_host_error.c_str(); }

@@ -1,0 +1,245 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the reference's golden vectors and the oracle.
+
+Bar (BASELINE.json north_star): <= 1e-10 relative per momentum bin, exact zeros where the reference has exact zeros,
+integer bookkeeping (species order, skipped / breakdown cell counts) exact.
+"""
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from common import REL_TOL, compare, golden_names, jonah_tables, load_golden, problem_from_recipe, surface_columns
+from is3d_b200 import api, synthetic, tables, workdir
+
+pytestmark = pytest.mark.gpu
+
+SUPPORTED_DF = (1, 2)
+
+
+def _supported(name):
+    return load_golden(name)["recipe"]["params"]["df_mode"] in SUPPORTED_DF
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    api.init()
+    yield
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if _supported(n)])
+def test_golden_vectors(name, fx):
+    gold = load_golden(name)
+    fl, cells, sp, g, tab, gla = problem_from_recipe(gold["recipe"], fx)
+    dN, st = api.smooth_spectra(fl, cells, sp, g, tab, gla)
+    rep = compare(dN, gold["dN"])
+    assert rep["ok"], rep
+    assert st["cells_skipped_udsigma"] == 0
+    assert st["cells_feqmod_breakdown"] == int(gold["breakdown"])
+    assert st["gpu_launches"] >= 3
+
+
+@pytest.mark.parametrize("n_cells", [1, 15, 17, 1000])
+@pytest.mark.parametrize("df_mode", [1, 2])
+def test_ragged_sizes_against_oracle(fx, n_cells, df_mode):
+    from oracle import cf_oracle as cfo
+    cols = synthetic.surface_vh(n_cells, 31 + n_cells)
+    cells = synthetic.columns_to_cells(cols, 1)
+    sp = tables.species(fx, 1, [211, -2212, 3334, 321, 2112]); g = tables.grid(fx); tab = tables.df_tables(fx, 1)
+    fl = tables.flags(df_mode=df_mode, dimension=3)
+    ref, _, _ = cfo.smooth(fl, cells, sp, g, tab, None)
+    for variant, chunks in ((0, 0), (2, 1), (5, 3), (7, 7)):
+        dN, st = api.smooth_spectra(fl, cells, sp, g, tab, None, tile_variant=variant, n_chunks=chunks)
+        rep = compare(dN, ref)
+        assert rep["ok"], (variant, chunks, rep)
+
+
+def test_nonstandard_grid_sizes(fx):
+    """pT / phi / y tables whose lengths are not multiples of the register tiles"""
+    from oracle import cf_oracle as cfo
+    g0 = tables.grid(fx)
+    g = dict(g0)
+    g["pT"] = g0["pT"][:13]; g["phi"] = g0["phi"][:5]; g["phi_weight"] = g0["phi_weight"][:5]; g["y"] = g0["y"][3:12]
+    cells = synthetic.columns_to_cells(synthetic.surface_vh(40, 77), 1)
+    sp = tables.species(fx, 1, "chosen_pikp"); tab = tables.df_tables(fx, 1)
+    fl = tables.flags(df_mode=1, dimension=3)
+    ref, _, _ = cfo.smooth(fl, cells, sp, g, tab, None)
+    for variant in (0, 1, 5):
+        dN, _ = api.smooth_spectra(fl, cells, sp, g, tab, None, tile_variant=variant)
+        assert compare(dN, ref)["ok"], variant
+
+
+def test_skipped_cells_and_counts(fx):
+    gold = load_golden("s3_df1")
+    fl, cells, sp, g, tab, gla = problem_from_recipe(gold["recipe"], fx)
+    bad = {k: np.concatenate([v[:7], v]) for k, v in cells.items()}
+    for k in ("dat", "dax", "day", "dan"):
+        bad[k][:7] *= -1.0                                            # u.dsigma < 0 for the first seven cells
+    dN, st = api.smooth_spectra(fl, bad, sp, g, tab, gla)
+    assert st["cells_skipped_udsigma"] == 7
+    assert compare(dN, gold["dN"])["ok"]
+
+
+def test_empty_surface_and_accumulate(fx):
+    gold = load_golden("s3_df2")
+    fl, cells, sp, g, tab, gla = problem_from_recipe(gold["recipe"], fx)
+    empty = {k: v[:0] for k, v in cells.items()}
+    dN, st = api.smooth_spectra(fl, empty, sp, g, tab, gla)
+    assert not dN.any() and st["evaluations"] == 0
+    # the result is ADDED into the caller's array (reference: += into dN_pTdpTdphidy)
+    out = np.full(gold["dN"].size, 1.0)
+    api.smooth_spectra(fl, cells, sp, g, tab, gla, out=out)
+    assert compare(out - 1.0, gold["dN"], tol=1e-9)["max_rel"] < 1e-6   # (1 + x) - 1 loses digits for tiny bins only
+    big = gold["dN"] > 1e-3
+    assert np.max(np.abs((out - 1.0)[big] - gold["dN"][big]) / gold["dN"][big]) < 1e-12
+
+
+def test_device_memory_path_is_identical(fx):
+    import torch
+    gold = load_golden("s3_df1")
+    fl, cells, sp, g, tab, gla = problem_from_recipe(gold["recipe"], fx)
+    host, _ = api.smooth_spectra(fl, cells, sp, g, tab, gla)
+    dev_cells = {k: torch.tensor(v, device="cuda") for k, v in cells.items()}
+    dev, _ = api.smooth_spectra(fl, dev_cells, sp, g, tab, gla, memory="device")
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.cpu().numpy(), host)
+
+
+def test_error_codes(fx):
+    gold = load_golden("s3_df1")
+    fl, cells, sp, g, tab, gla = problem_from_recipe(gold["recipe"], fx)
+    hot = dict(cells); hot["T"] = cells["T"].copy(); hot["T"][3] = 0.25            # outside the 0.100-0.200 GeV table
+    with pytest.raises(api.Is3dError) as e:
+        api.smooth_spectra(fl, hot, sp, g, tab, gla)
+    assert e.value.code == 3
+    with pytest.raises(api.Is3dError) as e:
+        api.smooth_spectra(dict(fl, include_baryon=1), cells, sp, g, tab, gla)
+    assert e.value.code == 2
+    with pytest.raises(api.Is3dError) as e:
+        api.smooth_spectra(dict(fl, dimension=4), cells, sp, g, tab, gla)
+    assert e.value.code == 1
+
+
+# ---------------------------------------------------------------------------------------- full-size properties
+@pytest.fixture(scope="module")
+def big(fx):
+    import torch
+    n = 20000
+    cells = synthetic.columns_to_cells(synthetic.surface_vh(n, synthetic.SEEDS["cfg3"]), 1)
+    sp = tables.species(fx, 1, "chosen_urqmd"); g = tables.grid(fx); tab = tables.df_tables(fx, 1)
+    dev = {k: torch.tensor(v, device="cuda") for k, v in cells.items()}
+    return cells, dev, sp, g, tab
+
+
+@pytest.mark.parametrize("df_mode", [1, 2])
+def test_full_pdg_linearity_and_order_invariance(big, df_mode):
+    """305 species x 16128 momentum bins: spectra(A u B) = spectra(A) + spectra(B), and cell order does not matter."""
+    import torch
+    cells, dev, sp, g, tab = big
+    fl = tables.flags(df_mode=df_mode, dimension=3)
+    full, st = api.smooth_spectra(fl, dev, sp, g, tab, None, memory="device")
+    n = dev["tau"].numel(); h = n // 3
+    a, _ = api.smooth_spectra(fl, {k: v[:h].contiguous() for k, v in dev.items()}, sp, g, tab, None, memory="device")
+    b, _ = api.smooth_spectra(fl, {k: v[h:].contiguous() for k, v in dev.items()}, sp, g, tab, None, memory="device")
+    perm = torch.randperm(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    p, _ = api.smooth_spectra(fl, {k: v[perm].contiguous() for k, v in dev.items()}, sp, g, tab, None, memory="device")
+    torch.cuda.synchronize()
+    full = full.cpu().numpy(); s = (a + b).cpu().numpy(); p = p.cpu().numpy()
+    assert np.all(full >= 0) and np.isfinite(full).all()
+    assert st["evaluations"] == n * 305 * 32 * 24 * 21
+    nz = full != 0
+    assert np.array_equal(s != 0, nz) and np.array_equal(p != 0, nz)
+    assert np.max(np.abs(s[nz] - full[nz]) / full[nz]) < 1e-12            # all terms >= 0: only summation-order ulps
+    assert np.max(np.abs(p[nz] - full[nz]) / full[nz]) < 1e-12
+
+
+def test_full_pdg_homogeneity_exact(big):
+    """dsigma -> 2 dsigma doubles every bin exactly (power-of-two scaling commutes with every rounding)."""
+    import torch
+    cells, dev, sp, g, tab = big
+    fl = tables.flags(df_mode=1, dimension=3)
+    sub = {k: v[:4000].contiguous() for k, v in dev.items()}
+    one, _ = api.smooth_spectra(fl, sub, sp, g, tab, None, memory="device")
+    two_cells = dict(sub)
+    for k in ("dat", "dax", "day", "dan"):
+        two_cells[k] = sub[k] * 2.0
+    two, _ = api.smooth_spectra(fl, two_cells, sp, g, tab, None, memory="device")
+    torch.cuda.synchronize()
+    assert torch.equal(two, one * 2.0)
+
+
+def test_sampled_bins_against_oracle_at_full_species(big, fx):
+    """oracle on a 64-cell prefix, all 305 species (4.9 M bins)"""
+    from oracle import cf_oracle as cfo
+    cells, dev, sp, g, tab = big
+    sub = {k: v[:64] for k, v in cells.items()}
+    fl = tables.flags(df_mode=1, dimension=3)
+    ref, _, _ = cfo.smooth(fl, sub, sp, g, tab, None)
+    dN, _ = api.smooth_spectra(fl, sub, sp, g, tab, None)
+    rep = compare(dN, ref)
+    assert rep["ok"], rep
+
+
+def test_two_plus_one_d_against_oracle(fx):
+    from oracle import cf_oracle as cfo
+    cells = synthetic.columns_to_cells(synthetic.surface_vh(300, synthetic.SEEDS["cfg2"], three_d=False, viscous=False), 1)
+    sp = tables.species(fx, 1, "chosen_pikp"); g = tables.grid(fx); tab = tables.df_tables(fx, 1)
+    fl = tables.flags(df_mode=1, dimension=2, include_bulk=0, include_shear=0)
+    ref, _, _ = cfo.smooth(fl, cells, sp, g, tab, None)
+    for variant in (0, 3):
+        dN, st = api.smooth_spectra(fl, cells, sp, g, tab, None, tile_variant=variant)
+        assert compare(dN, ref)["ok"]
+        assert st["evaluations"] == 300 * 3 * 32 * 24 * 241
+
+
+# ---------------------------------------------------------------------------------------- file interface end to end
+@pytest.mark.parametrize("name", ["toy_df1", "s2_df1"])
+def test_run_workdir_end_to_end(fx, name):
+    gold = load_golden(name)
+    lib = api.lib()
+    with tempfile.TemporaryDirectory() as wd:
+        workdir.materialize(wd, surface_columns=surface_columns(gold["recipe"], fx), chosen=gold["recipe"]["chosen"], fixture=fx,
+                            operation=1, mode=1, **gold["recipe"]["params"])
+        dN = np.zeros(gold["dN"].size); mcid = np.zeros(8, dtype=np.int32); st = api.Stats()
+        rc = lib.is3d_b200_run_workdir(wd.encode(), dN.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(dN.size),
+                                       mcid.ctypes.data_as(C.POINTER(C.c_int32)), 8, C.byref(st))
+        assert rc == 0
+        assert list(mcid[:3]) == list(gold["mcid"])
+        assert compare(dN, gold["dN"])["ok"]
+        assert open(os.path.join(wd, "average_thermodynamic_quantities.dat")).read() == str(gold["averages_file"])
+        for rel in gold["file_sha256"]:
+            assert os.path.getsize(os.path.join(wd, rel)) > 0
+        # text output carries 9 significant digits: compare parsed values
+        rows = np.loadtxt(os.path.join(wd, "results", "dN_pTdpTdphidy_211.dat"), skiprows=1)
+        y_pts = 1 if gold["recipe"]["params"]["dimension"] == 2 else 21
+        ref = gold["dN"].reshape(21, 24, 32, 3)[:y_pts, :, :, 0].ravel()
+        assert rows.shape == (y_pts * 24 * 32, 4)
+        nz = ref != 0
+        assert np.max(np.abs(rows[nz, 3] - ref[nz]) / ref[nz]) < 2e-8
+
+
+def test_executable_runs(fx):
+    import subprocess
+    exe = os.path.join(os.path.dirname(api.LIB_PATH), "is3d_b200_run")
+    if not os.path.exists(exe):
+        pytest.skip("executable not built")
+    with tempfile.TemporaryDirectory() as wd:
+        workdir.materialize(wd, fixture=fx, operation=1, mode=1, hrg_eos=2, dimension=3, df_mode=1)
+        r = subprocess.run([exe], cwd=wd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert os.path.getsize(os.path.join(wd, "results", "dN_dy_211.dat")) > 0
+
+
+@pytest.mark.skipif("__import__('torch').cuda.device_count() < 2")
+def test_two_gpu_nccl(fx, tmp_path):
+    """2 ranks, one per GPU, NCCL all-reduce of the spectra: equals the 1-GPU result to summation-order ulps"""
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "nccl_worker.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29531", script, str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    d0 = np.load(tmp_path / "dN_0.npy"); ref = np.load(tmp_path / "dN_single.npy")
+    nz = ref != 0
+    assert np.max(np.abs(d0[nz] - ref[nz]) / ref[nz]) < 1e-12 and np.all(d0[~nz] == 0)
