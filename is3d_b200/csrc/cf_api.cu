@@ -44,12 +44,13 @@ struct DevBuf {
 };
 
 struct Workspace {
-  DevBuf raw, small, Y, P, S, partial, dN, counters, extra;
+  DevBuf raw, small, Y, P, S, Y2, P2, S2, partial, dN, counters, extra;
   cudaEvent_t ev[8];
   bool events = false;
   void release()
   {
-    raw.release(); small.release(); Y.release(); P.release(); S.release(); partial.release(); dN.release();
+    raw.release(); small.release(); Y.release(); P.release(); S.release(); Y2.release(); P2.release(); S2.release();
+    partial.release(); dN.release();
     counters.release(); extra.release();
     if (events) { for (auto &e : ev) cudaEventDestroy(e); events = false; }
   }
@@ -181,11 +182,21 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
   const bool vah = (fl->mode == 2);
   if (fl->dimension != 2 && fl->dimension != 3) return fail(IS3D_ERR_ARGUMENT, "dimension must be 2 or 3");
   if (sp->n <= 0 || gr->n_pT <= 0 || gr->n_phi <= 0 || gr->n_y <= 0) return fail(IS3D_ERR_ARGUMENT, "empty species list or momentum table");
+  if (!sp->mass || !sp->sign || !sp->degeneracy || !gr->pT || !gr->phi || !gr->y) return fail(IS3D_ERR_ARGUMENT, "NULL species or momentum table");
   if (fl->dimension == 2 && (gr->n_eta <= 0 || !gr->eta || !gr->eta_weight)) return fail(IS3D_ERR_ARGUMENT, "dimension = 2 needs the eta table");
   if (fl->include_baryon) return fail(IS3D_ERR_UNSUPPORTED, "include_baryon = 1 (the reference's (T, muB) lookup reads out of bounds, SURVEY R8)");
-  if (vah) return fail(IS3D_ERR_UNSUPPORTED, "mode 2 (anisotropic) kernel not built yet");
-  if (fl->df_mode != 1 && fl->df_mode != 2) return fail(IS3D_ERR_UNSUPPORTED, "df_mode 3/4 (feqmod) kernel not built yet");
-  if (!df || df->n_T < 3) return fail(IS3D_ERR_ARGUMENT, "delta-f coefficient tables missing");
+  if (!vah && (fl->df_mode < 1 || fl->df_mode > 4)) return fail(IS3D_ERR_ARGUMENT, "df_mode must be 1..4");
+  if (!vah && (!df || df->n_T < 3 || !df->T)) return fail(IS3D_ERR_ARGUMENT, "delta-f coefficient tables missing");
+  const bool feqmod = !vah && (fl->df_mode == 3 || fl->df_mode == 4);
+  const int model = vah ? M_VAH : (fl->df_mode == 1 ? M_LIN14 : fl->df_mode == 2 ? M_LINCE : M_FEQMOD);
+  if (!vah) {
+    if (fl->df_mode == 1 && (!df->c0 || !df->c2)) return fail(IS3D_ERR_ARGUMENT, "df_mode 1 needs the c0 and c2 tables");
+    if ((fl->df_mode == 2 || fl->df_mode == 3) && (!df->F || !df->betabulk || !df->betapi)) return fail(IS3D_ERR_ARGUMENT, "df_mode 2/3 need the F, betabulk and betapi tables");
+    if (fl->df_mode == 4 && (!df->betapi || df->n_jonah < 3 || !df->jonah_x || !df->jonah_lambda2 || !df->jonah_z))
+      return fail(IS3D_ERR_ARGUMENT, "df_mode 4 needs betapi and the Jonah lambda/z tables");
+    if (fl->df_mode == 3 && (!gla || gla->n_points <= 0 || !gla->root1 || !gla->weight1 || !gla->root2 || !gla->weight2))
+      return fail(IS3D_ERR_ARGUMENT, "df_mode 3 needs the Gauss-Laguerre nodes");
+  }
   const int64_t n_cells = sf->n_cells;
   if (n_cells < 0) return fail(IS3D_ERR_ARGUMENT, "negative cell count");
   const bool dim2 = (fl->dimension == 2);
@@ -196,6 +207,7 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
   L.n_species = sp->n; L.n_pT = gr->n_pT; L.n_phi = gr->n_phi; L.n_y_out = gr->n_y;
   L.dim2 = dim2 ? 1 : 0;
   L.n_slots = dim2 ? gr->n_eta : gr->n_y;
+  L.rec_y = vah ? kRecVah : kRec;
   int variant = opt.tile_variant;
   if (variant < 0 || variant > 7) variant = 0;
   int nyt, npt, ct;
@@ -227,6 +239,7 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
     n_chunks = (int)((target_blocks + n_bintiles - 1) / n_bintiles);
     const int64_t max_partial_bytes = (int64_t)2 << 30;                 // keep the partial buffer <= 2 GiB
     int64_t cap = max_partial_bytes / (n_bins * 8 > 0 ? n_bins * 8 : 1);
+    if (feqmod) cap /= 2;
     if (cap < 1) cap = 1;
     if (n_chunks > cap) n_chunks = (int)cap;
   }
@@ -238,41 +251,66 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
   SmallArena ar;
   std::vector<double> cosphi(gr->n_phi), sinphi(gr->n_phi);
   for (int k = 0; k < gr->n_phi; k++) { cosphi[k] = cos(gr->phi[k]); sinphi[k] = sin(gr->phi[k]); }   // smooth_kernels.cpp:43-48
+  std::vector<double> zero_baryon(sp->n, 0.0);
   const size_t o_mass = ar.put(sp->mass, sp->n), o_sign = ar.put(sp->sign, sp->n), o_deg = ar.put(sp->degeneracy, sp->n);
+  const size_t o_bar = ar.put(sp->baryon ? sp->baryon : zero_baryon.data(), sp->n);
   const size_t o_pT = ar.put(gr->pT, gr->n_pT), o_cos = ar.put(cosphi.data(), gr->n_phi), o_sin = ar.put(sinphi.data(), gr->n_phi);
   const size_t o_sloty = dim2 ? ar.put(gr->eta, gr->n_eta) : ar.put(gr->y, gr->n_y);
   const size_t o_slotw = dim2 ? ar.put(gr->eta_weight, gr->n_eta) : 0;
-  const size_t o_T = ar.put(df->T, df->n_T);
-  struct SplineOff { size_t y, c; };
-  auto put_spline = [&](const double *y) {
-    SplineOff o{0, 0};
-    if (!y) return o;
-    std::vector<double> c(df->n_T);
-    host_spline_init(df->T, y, df->n_T, c.data());
-    o.y = ar.put(y, df->n_T); o.c = ar.put(c.data(), df->n_T);
+  struct SplineOff { size_t x, y, c; int n; };
+  auto put_spline = [&](const double *x, const double *y, int n) {
+    SplineOff o{0, 0, 0, 0};
+    if (!x || !y || n < 3) return o;
+    std::vector<double> c(n);
+    host_spline_init(x, y, n, c.data());
+    o.x = ar.put(x, n); o.y = ar.put(y, n); o.c = ar.put(c.data(), n); o.n = n;
     return o;
   };
-  const SplineOff s_c0 = put_spline(df->c0), s_c2 = put_spline(df->c2), s_F = put_spline(df->F),
-                  s_bb = put_spline(df->betabulk), s_bp = put_spline(df->betapi);
+  SplineOff s_c0{}, s_c2{}, s_F{}, s_bb{}, s_bp{}, s_l2{}, s_z{};
+  size_t o_r1 = 0, o_w1 = 0, o_r2 = 0, o_w2 = 0;
+  if (!vah) {
+    s_c0 = put_spline(df->T, df->c0, df->n_T); s_c2 = put_spline(df->T, df->c2, df->n_T); s_F = put_spline(df->T, df->F, df->n_T);
+    s_bb = put_spline(df->T, df->betabulk, df->n_T); s_bp = put_spline(df->T, df->betapi, df->n_T);
+    if (fl->df_mode == 4) { s_l2 = put_spline(df->jonah_x, df->jonah_lambda2, df->n_jonah); s_z = put_spline(df->jonah_x, df->jonah_z, df->n_jonah); }
+    if (fl->df_mode == 3) {
+      o_r1 = ar.put(gla->root1, gla->n_points); o_w1 = ar.put(gla->weight1, gla->n_points);
+      o_r2 = ar.put(gla->root2, gla->n_points); o_w2 = ar.put(gla->weight2, gla->n_points);
+    }
+  }
 
-  // ---- device buffers
-  const int n_raw = 18;
-  const double *raw_src[n_raw] = {sf->tau, sf->eta, sf->dat, sf->dax, sf->day, sf->dan, sf->ux, sf->uy, sf->un, sf->T, sf->P, sf->E,
-                                  sf->pixx, sf->pixy, sf->pixn, sf->piyy, sf->piyn, sf->bulkPi};
-  const bool need[n_raw] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
-                            (bool)fl->include_shear_deltaf, (bool)fl->include_shear_deltaf, (bool)fl->include_shear_deltaf,
-                            (bool)fl->include_shear_deltaf, (bool)fl->include_shear_deltaf, (bool)fl->include_bulk_deltaf};
+  // ---- raw surface arrays
+  const bool sh = fl->include_shear_deltaf != 0, bk = fl->include_bulk_deltaf != 0;
+  struct RawItem { const double *src; bool need; const double **dst; };
+  RawCells rc; memset(&rc, 0, sizeof(rc));
+  rc.n = n_cells;
+  RawItem items[] = {
+    {sf->tau, true, &rc.tau}, {sf->eta, true, &rc.eta}, {sf->dat, true, &rc.dat}, {sf->dax, true, &rc.dax}, {sf->day, true, &rc.day},
+    {sf->dan, true, &rc.dan}, {sf->ux, true, &rc.ux}, {sf->uy, true, &rc.uy}, {sf->un, true, &rc.un},
+    {sf->T, !vah, &rc.T}, {sf->P, !vah, &rc.P}, {sf->E, !vah, &rc.E},
+    {sf->pixx, vah || sh, &rc.pixx}, {sf->pixy, vah || sh, &rc.pixy}, {sf->pixn, vah || sh, &rc.pixn}, {sf->piyy, vah || sh, &rc.piyy},
+    {sf->piyn, vah || sh, &rc.piyn}, {sf->bulkPi, vah ? bk : bk, &rc.bulkPi},
+    {sf->pitt, vah, &rc.pitt}, {sf->pitx, vah, &rc.pitx}, {sf->pity, vah, &rc.pity}, {sf->pitn, vah, &rc.pitn}, {sf->pinn, vah, &rc.pinn},
+    {sf->Wx, vah, &rc.Wx}, {sf->Wy, vah, &rc.Wy}, {sf->Lambda, vah, &rc.Lambda}, {sf->aL, vah, &rc.aL},
+    {sf->c0, vah, &rc.c0}, {sf->c1, vah, &rc.c1}, {sf->c2, vah, &rc.c2}, {sf->c3, vah, &rc.c3}, {sf->c4, vah, &rc.c4}};
+  const int n_raw = (int)(sizeof(items) / sizeof(items[0]));
   for (int a = 0; a < n_raw; a++)
-    if (need[a] && !raw_src[a] && n_cells > 0) return fail(IS3D_ERR_ARGUMENT, "a required surface array is NULL");
+    if (items[a].need && !items[a].src && n_cells > 0) return fail(IS3D_ERR_ARGUMENT, "a required surface array is NULL");
 
-  const size_t rec_Y = (size_t)L.n_ytiles * L.n_cells_pad * L.nst * kRec * 8;
+  const size_t rec_Y = (size_t)L.n_ytiles * L.n_cells_pad * L.nst * L.rec_y * 8;
   const size_t rec_P = (size_t)L.n_ptiles * L.n_cells_pad * L.npt * kRec * 8;
   const size_t rec_S = (size_t)L.n_cells_pad * kScal * 8;
+  const int partial_sets = feqmod ? 2 : 1;
   CU_CHECK(g_ws.small.reserve(ar.host.size() + 256));
   CU_CHECK(g_ws.Y.reserve(rec_Y + 256));
   CU_CHECK(g_ws.P.reserve(rec_P + 256));
   CU_CHECK(g_ws.S.reserve(rec_S + 256));
-  CU_CHECK(g_ws.partial.reserve((size_t)n_chunks * n_bins * 8 + 256));
+  if (feqmod) {
+    CU_CHECK(g_ws.Y2.reserve(rec_Y + 256));
+    CU_CHECK(g_ws.P2.reserve(rec_P + 256));
+    CU_CHECK(g_ws.S2.reserve(rec_S + 256));
+    if (fl->df_mode == 3) CU_CHECK(g_ws.extra.reserve(((size_t)L.n_species + 8) * L.n_cells_pad * 8 + 256));
+  }
+  CU_CHECK(g_ws.partial.reserve((size_t)partial_sets * n_chunks * n_bins * 8 + 256));
   CU_CHECK(g_ws.counters.reserve(256));
   const size_t cell_stride = ((size_t)n_cells * 8 + 255) & ~(size_t)255;
   if (opt.memory == 0) {
@@ -285,21 +323,15 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
   // ---- host -> device
   unsigned char *small_d = g_ws.small.as<unsigned char>();
   CU_CHECK(cudaMemcpyAsync(small_d, ar.host.data(), ar.host.size(), cudaMemcpyHostToDevice, st));
-  RawCells rc; memset(&rc, 0, sizeof(rc));
-  rc.n = n_cells;
-  const double *raw_dev[n_raw];
   for (int a = 0; a < n_raw; a++) {
-    raw_dev[a] = nullptr;
-    if (!need[a] || n_cells == 0) continue;
+    *items[a].dst = nullptr;
+    if (!items[a].need || n_cells == 0) continue;
     if (opt.memory == 0) {
       double *dst = reinterpret_cast<double *>(g_ws.raw.as<unsigned char>() + cell_stride * a);
-      CU_CHECK(cudaMemcpyAsync(dst, raw_src[a], (size_t)n_cells * 8, cudaMemcpyHostToDevice, st));
-      raw_dev[a] = dst;
-    } else raw_dev[a] = raw_src[a];
+      CU_CHECK(cudaMemcpyAsync(dst, items[a].src, (size_t)n_cells * 8, cudaMemcpyHostToDevice, st));
+      *items[a].dst = dst;
+    } else *items[a].dst = items[a].src;
   }
-  rc.tau = raw_dev[0]; rc.eta = raw_dev[1]; rc.dat = raw_dev[2]; rc.dax = raw_dev[3]; rc.day = raw_dev[4]; rc.dan = raw_dev[5];
-  rc.ux = raw_dev[6]; rc.uy = raw_dev[7]; rc.un = raw_dev[8]; rc.T = raw_dev[9]; rc.P = raw_dev[10]; rc.E = raw_dev[11];
-  rc.pixx = raw_dev[12]; rc.pixy = raw_dev[13]; rc.pixn = raw_dev[14]; rc.piyy = raw_dev[15]; rc.piyn = raw_dev[16]; rc.bulkPi = raw_dev[17];
   double *dN_dev = (opt.memory == 0) ? g_ws.dN.as<double>() : dN_out;
   if (opt.memory == 0) CU_CHECK(cudaMemsetAsync(dN_dev, 0, (size_t)n_bins * 8, st));
   CU_CHECK(cudaMemsetAsync(g_ws.counters.p, 0, sizeof(PrepCounters), st));
@@ -308,42 +340,72 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
   // ---- prepare
   auto dptr = [&](size_t off) { return reinterpret_cast<const double *>(small_d + off); };
   PrepTables tab; memset(&tab, 0, sizeof(tab));
-  auto mk = [&](const SplineOff &o) { Spline s; s.x = dptr(o_T); s.y = dptr(o.y); s.c = dptr(o.c); s.n = df->n_T; return s; };
-  tab.c0 = mk(s_c0); tab.c2 = mk(s_c2); tab.F = mk(s_F); tab.betabulk = mk(s_bb); tab.betapi = mk(s_bp);
+  auto mk = [&](const SplineOff &o) { Spline s; s.x = dptr(o.x); s.y = dptr(o.y); s.c = dptr(o.c); s.n = o.n; return s; };
+  tab.c0 = mk(s_c0); tab.c2 = mk(s_c2); tab.F = mk(s_F); tab.betabulk = mk(s_bb); tab.betapi = mk(s_bp); tab.lam2 = mk(s_l2); tab.z = mk(s_z);
+  tab.bulkPi_over_Peq_max = df ? df->bulkPi_over_Peq_max : 0.0;
   tab.cosphi = dptr(o_cos); tab.sinphi = dptr(o_sin); tab.slot_y = dptr(o_sloty); tab.slot_w = dim2 ? dptr(o_slotw) : nullptr;
-  if (fl->df_mode == 1 && (!df->c0 || !df->c2)) return fail(IS3D_ERR_ARGUMENT, "df_mode 1 needs the c0 and c2 tables");
-  if (fl->df_mode == 2 && (!df->F || !df->betabulk || !df->betapi)) return fail(IS3D_ERR_ARGUMENT, "df_mode 2 needs the F, betabulk and betapi tables");
-  CU_CHECK(launch_prepare_vh(*fl, rc, tab, L, g_ws.Y.as<double>(), g_ws.P.as<double>(), g_ws.S.as<double>(),
-                             g_ws.counters.as<PrepCounters>(), st));
-  stt.gpu_launches++;
+  tab.gla_root1 = dptr(o_r1); tab.gla_w1 = dptr(o_w1); tab.gla_root2 = dptr(o_r2); tab.gla_w2 = dptr(o_w2); tab.gla_n = gla ? gla->n_points : 0;
+  tab.deta_min = fl->deta_min; tab.mass_pion0 = fl->mass_pion0;
+  tab.eta_delta = (dim2 && gr->n_eta > 1) ? gr->eta[1] - gr->eta[0] : 0.0;                    // smooth_kernels.cpp:2175
+  PrepCounters *cnt_d = g_ws.counters.as<PrepCounters>();
+  if (vah) {
+    CU_CHECK(launch_prepare_vah(*fl, rc, tab, L, g_ws.Y.as<double>(), g_ws.P.as<double>(), g_ws.S.as<double>(), cnt_d, st));
+    stt.gpu_launches++;
+  } else if (feqmod) {
+    CU_CHECK(launch_prepare_feqmod(*fl, rc, tab, L, g_ws.Y.as<double>(), g_ws.P.as<double>(), g_ws.S.as<double>(),
+                                   g_ws.Y2.as<double>(), g_ws.P2.as<double>(), g_ws.S2.as<double>(),
+                                   dptr(o_mass), dptr(o_sign), dptr(o_deg), dptr(o_bar),
+                                   fl->df_mode == 3 ? g_ws.extra.as<double>() : nullptr, cnt_d, st));
+    stt.gpu_launches += (fl->df_mode == 3) ? 2 : 1;
+  } else {
+    CU_CHECK(launch_prepare_vh(*fl, rc, tab, L, g_ws.Y.as<double>(), g_ws.P.as<double>(), g_ws.S.as<double>(), cnt_d, st));
+    stt.gpu_launches++;
+  }
   CU_CHECK(cudaEventRecord(ev[2], st));
 
-  // ---- hot kernel
+  // ---- hot kernel(s)
   HotParams hp; memset(&hp, 0, sizeof(hp));
   hp.L = L; hp.Y = g_ws.Y.as<double>(); hp.P = g_ws.P.as<double>(); hp.S = g_ws.S.as<double>();
   hp.mass = dptr(o_mass); hp.sign = dptr(o_sign); hp.degeneracy = dptr(o_deg); hp.pT = dptr(o_pT);
   hp.partial = g_ws.partial.as<double>();
+  hp.renorm = (feqmod && fl->df_mode == 3) ? g_ws.extra.as<double>() : nullptr;
   hp.n_chunks = n_chunks; hp.n_groupblocks = n_groupblocks; hp.n_warps = n_warps;
   hp.regulate_thr = fl->regulate_deltaf ? 0x3ff00000 : 0x7ff80000;
-  hp.outflow_thr = fl->outflow ? 0LL : (long long)0x8000000000000000ULL;
-  hp.prefactor = pow(2.0 * M_PI * 0.197327053, -3);                    // smooth_kernels.cpp:36
-  CU_CHECK(launch_hot_vh(*fl, hp, variant, st, nullptr));
+  hp.outflow_thr = (fl->outflow && !vah) ? 0LL : (long long)0x8000000000000000ULL;   // the anisotropic kernel has no Theta(p.dsigma)
+  const double hbarC = 0.197327053;
+  hp.prefactor = vah ? 1.0 / (8.0 * (M_PI * M_PI * M_PI)) / hbarC / hbarC / hbarC      // smooth_kernels.cpp:2146
+                     : pow(2.0 * M_PI * hbarC, -3);                                      // :36, :400
+  CU_CHECK(launch_hot(model, hp, variant, st, nullptr));
   stt.gpu_launches++;
+  int reduce_sets = 1;
+  PrepCounters cnt; memset(&cnt, 0, sizeof(cnt));
+  if (feqmod) {
+    // cells where feqmod breaks down (and narrow-rapidity slots) take the linear-df branch: second pass, only if any
+    CU_CHECK(cudaMemcpyAsync(&cnt, cnt_d, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    if (cnt.linear_items > 0) {
+      HotParams hl = hp;
+      hl.Y = g_ws.Y2.as<double>(); hl.P = g_ws.P2.as<double>(); hl.S = g_ws.S2.as<double>();
+      hl.partial = hp.partial + (size_t)n_chunks * n_bins; hl.renorm = nullptr;
+      CU_CHECK(launch_hot(fl->df_mode == 3 ? M_LINCE : M_JONAHLIN, hl, variant, st, nullptr));
+      stt.gpu_launches++;
+      reduce_sets = 2;
+    }
+  }
   CU_CHECK(cudaEventRecord(ev[3], st));
 
   // ---- reduce chunks, add into the result
-  CU_CHECK(launch_reduce(hp.partial, n_chunks, n_bins, dN_dev, st));
+  CU_CHECK(launch_reduce(hp.partial, n_chunks * reduce_sets, n_bins, dN_dev, st));
   stt.gpu_launches++;
   CU_CHECK(cudaEventRecord(ev[4], st));
 
   // ---- device -> host
-  PrepCounters cnt; memset(&cnt, 0, sizeof(cnt));
   std::vector<double> host_dN;
   if (opt.memory == 0) {
     host_dN.resize((size_t)n_bins);
     CU_CHECK(cudaMemcpyAsync(host_dN.data(), dN_dev, (size_t)n_bins * 8, cudaMemcpyDeviceToHost, st));
   }
-  CU_CHECK(cudaMemcpyAsync(&cnt, g_ws.counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+  CU_CHECK(cudaMemcpyAsync(&cnt, cnt_d, sizeof(cnt), cudaMemcpyDeviceToHost, st));
   CU_CHECK(cudaEventRecord(ev[5], st));
   CU_CHECK(cudaEventSynchronize(ev[5]));
   if (opt.memory == 0)
@@ -361,8 +423,7 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
   stt.evaluations = n_cells * (int64_t)sp->n * gr->n_pT * gr->n_phi * (dim2 ? (int64_t)gr->n_eta : (int64_t)gr->n_y);
   stt.n_chunks = n_chunks; stt.tile_variant = variant;
   if (stats) *stats = stt;
-  if (cnt.range_error) return fail(IS3D_ERR_TABLE_RANGE, "cell temperature outside the delta-f coefficient table");
-  (void)gla;
+  if (cnt.range_error) return fail(IS3D_ERR_TABLE_RANGE, "a cell's T or Pi/P lies outside the delta-f coefficient table (or T_mod <= 0)");
   return IS3D_OK;
 }
 

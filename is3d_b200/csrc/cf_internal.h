@@ -6,7 +6,8 @@
 
 namespace is3d {
 
-constexpr int kRec = 6;          // doubles per slot / phi record
+constexpr int kRec = 6;          // doubles per phi record (and per slot record, except the anisotropic model)
+constexpr int kRecVah = 8;       // doubles per slot record of the anisotropic model
 constexpr int kScal = 4;         // doubles per per-cell scalar record
 constexpr int kMaxWarps = 4;     // warps per hot-kernel block (each warp = 32 consecutive (species, pT) pairs)
 constexpr int kStages = 4;       // TMA pipeline depth
@@ -29,6 +30,7 @@ struct PrepTables {
   const double *slot_y;                 // 3+1D: y values [n_y];  2+1D: eta values [n_eta]
   const double *slot_w;                 // 2+1D: eta weights [n_eta]; 3+1D: NULL
   const double *gla_root1, *gla_w1, *gla_root2, *gla_w2; int gla_n;   // feqmod
+  double deta_min, mass_pion0, eta_delta;                              // eta_delta: spacing of the eta table (anisotropic 2+1D weights)
 };
 
 // Geometry of the tiled record arrays
@@ -40,17 +42,28 @@ struct Layout {
   int n_slots;                           // rapidity slots per cell: n_y (3+1D) or n_eta (2+1D)
   int dim2;
   int nst, n_ytiles, npt, n_ptiles;
+  int rec_y;                             // doubles per slot record (kRec or kRecVah)
   int ct;                                // cells per TMA tile
   int64_t n_cells, n_cells_pad, n_tiles;
 };
 
-struct PrepCounters { unsigned long long skipped, breakdown, range_error; };
+struct PrepCounters { unsigned long long skipped, breakdown, range_error, linear_items; };
+
+// distribution-function models of the hot kernel
+enum Model {
+  M_LIN14 = 1,      // f_eq (1 + df), 14-moment            (smooth_kernels.cpp:303-312)
+  M_LINCE = 2,      // f_eq (1 + df), Chapman-Enskog       (:313-321, also the df_mode 3 breakdown branch :835-857)
+  M_FEQMOD = 3,     // modified equilibrium, Mike / Jonah  (:878-928)
+  M_JONAHLIN = 4,   // Jonah's linearised df, breakdown branch of df_mode 4 (:858-876)
+  M_VAH = 5         // anisotropic f_a (1 + df~), PL matching (:2297-2349)
+};
 
 struct HotParams {
   Layout L;
   const double *Y, *P, *S;
   const double *mass, *sign, *degeneracy, *pT;    // species / pT tables on device
   double *partial;                                 // [n_chunks][n_bins]
+  const double *renorm;                            // feqmod, df_mode 3: [n_species][n_cells_pad]; NULL -> per-cell value in S[1]
   int n_chunks, n_groupblocks, n_warps;
   long long outflow_thr;                           // bit pattern threshold of the p.dsigma > 0 test
   double prefactor;
@@ -60,7 +73,13 @@ struct HotParams {
 // launchers (cf_prepare.cu / cf_kernels.cu)
 cudaError_t launch_prepare_vh(const is3d_flags &fl, const RawCells &cells, const PrepTables &tab, const Layout &L,
                               double *Y, double *P, double *S, PrepCounters *counters, cudaStream_t st);
-cudaError_t launch_hot_vh(const is3d_flags &fl, const HotParams &hp, int variant, cudaStream_t st, size_t *smem_out);
+cudaError_t launch_prepare_feqmod(const is3d_flags &fl, const RawCells &cells, const PrepTables &tab, const Layout &L,
+                                  double *YF, double *PF, double *SF, double *YL, double *PL, double *SL,
+                                  const double *mass, const double *sign, const double *degeneracy, const double *baryon,
+                                  double *renorm, PrepCounters *counters, cudaStream_t st);
+cudaError_t launch_prepare_vah(const is3d_flags &fl, const RawCells &cells, const PrepTables &tab, const Layout &L,
+                               double *Y, double *P, double *S, PrepCounters *counters, cudaStream_t st);
+cudaError_t launch_hot(int model, const HotParams &hp, int variant, cudaStream_t st, size_t *smem_out);
 cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, double *out, cudaStream_t st);
 cudaError_t launch_fp64_peak(double *sink, int iters, cudaStream_t st, int *blocks, int *threads, long long *dfma_per_thread);
 void hot_variant_shape(int variant, int dim2, int *nyt, int *npt, int *ct);

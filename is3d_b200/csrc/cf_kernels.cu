@@ -20,34 +20,33 @@
 
 namespace is3d {
 
-// one evaluation: returns f_eq (1 + df); x = u.p/T - chem, s = partial delta-f polynomial
-template <int DFM>
-__device__ __forceinline__ double distribution(double x, double s, double K2, double sign, int reg_thr)
+// Bose/Fermi factor 1 / (e^x + Theta) from a = e^{-x}
+__device__ __forceinline__ double occupation(double a, double sign) { return a * rcp_fast(fma(sign, a, 1.0)); }
+
+// f_eq (1 + df) of the linear-df models; x = u.p/T, s = partial delta-f polynomial (see cf_prepare.cu)
+template <int MODEL>
+__device__ __forceinline__ double distribution(double x, double s, double K2, double K3, double sign, int reg_thr)
 {
   double dfs;
-  if (DFM == 1) {
-    dfs = fma(K2 * x, x, s);                      // + Pi bulk2 (u.p)^2
-  } else {
-    dfs = fma(s, rcp_fast(x), K2 * x);            // [..]/(u.p) + Pi (bulk0 + bulk2) (u.p)
-  }
-  const double a = exp_neg(x);                    // e^{-x}
-  const double b = fma(sign, a, 1.0);             // 1 + Theta e^{-x}
-  const double feq = a * rcp_fast(b);             // 1 / (e^{x} + Theta)
+  if (MODEL == M_LIN14) dfs = fma(K2 * x, x, s);               // + Pi bulk2 (u.p)^2
+  else dfs = fma(s, rcp_fast(x), K2 * x);                      // [..]/(u.p) + (..)(u.p)
+  const double feq = occupation(exp_neg(x), sign);
   const double feqbar = fma(-sign, feq, 1.0);
-  double df = feqbar * dfs;
-  df = clamp_unit(df, reg_thr);                   // regulate_deltaf
+  double df = (MODEL == M_JONAHLIN) ? fma(feqbar, dfs, K3) : feqbar * dfs;
+  df = clamp_unit(df, reg_thr);                                // regulate_deltaf
   return fma(feq, df, feq);
 }
 
-template <int DFM, int NYT, int NPT, bool DIM2, int MINB>
+template <int MODEL, int NYT, int NPT, bool DIM2, int MINB>
 __global__ void __launch_bounds__(kMaxWarps * 32, MINB)
-cf_vh_kernel(const HotParams hp)
+cf_kernel(const HotParams hp)
 {
+  constexpr int RY = (MODEL == M_VAH) ? kRecVah : kRec;       // doubles per slot record
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const Layout &L = hp.L;
-  const int nst = DIM2 ? L.nst : NYT;             // slots per cell in this block's tile
+  const int nst = DIM2 ? L.nst : NYT;                         // slots per cell in this block's tile
   const int CT = L.ct;
-  const int y_doubles = CT * nst * kRec, p_doubles = CT * NPT * kRec, s_doubles = CT * kScal;
+  const int y_doubles = CT * nst * RY, p_doubles = CT * NPT * kRec, s_doubles = CT * kScal;
   const int stage_doubles = y_doubles + p_doubles + s_doubles;
   double *stage_base = reinterpret_cast<double *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(stage_base + (size_t)kStages * stage_doubles);
@@ -72,13 +71,14 @@ cf_vh_kernel(const HotParams hp)
   const double mT = sqrt(mT2);
   const int reg_thr = hp.regulate_thr;
   const long long thr = hp.outflow_thr;
+  const double *renorm = (MODEL == M_FEQMOD && hp.renorm) ? hp.renorm + (int64_t)ipart * L.n_cells_pad : nullptr;
 
   // ---- cell tiles of this chunk: balanced contiguous split of [0, n_tiles)
   const int64_t t_begin = (L.n_tiles * (int64_t)chunk) / hp.n_chunks;
   const int64_t t_end = (L.n_tiles * (int64_t)(chunk + 1)) / hp.n_chunks;
   const int n_my_tiles = (int)(t_end - t_begin);
 
-  const double *Yg = hp.Y + ((int64_t)ty * L.n_cells_pad) * nst * kRec;
+  const double *Yg = hp.Y + ((int64_t)ty * L.n_cells_pad) * nst * RY;
   const double *Pg = hp.P + ((int64_t)tp * L.n_cells_pad) * NPT * kRec;
   const double *Sg = hp.S;
   const uint32_t stage_bytes = (uint32_t)stage_doubles * 8u;
@@ -94,7 +94,7 @@ cf_vh_kernel(const HotParams hp)
     const int64_t cell = (t_begin + t_local) * CT;
     double *dst = stage_base + (size_t)st * stage_doubles;
     mbar_arrive_expect_tx(&full[st], stage_bytes);
-    bulk_g2s(dst, Yg + cell * nst * kRec, (uint32_t)y_doubles * 8u, &full[st]);
+    bulk_g2s(dst, Yg + cell * nst * RY, (uint32_t)y_doubles * 8u, &full[st]);
     bulk_g2s(dst + y_doubles, Pg + cell * NPT * kRec, (uint32_t)p_doubles * 8u, &full[st]);
     bulk_g2s(dst + y_doubles + p_doubles, Sg + cell * kScal, (uint32_t)s_doubles * 8u, &full[st]);
   };
@@ -112,60 +112,96 @@ cf_vh_kernel(const HotParams hp)
     const double *Ys = stage_base + (size_t)st * stage_doubles;
     const double *Ps = Ys + y_doubles;
     const double *Ss = Ps + p_doubles;
+    const int64_t cell_base = (t_begin + t) * CT;
 
     for (int c = 0; c < CT; c++) {
-      const double2 k02 = *reinterpret_cast<const double2 *>(Ss + c * kScal);
-      const double K0m = k02.x * m2, K2 = k02.y;
-      // phi hoists: 5 multiplies per (cell, phi), reused by every slot
-      double q[NPT], pd[NPT], g0[NPT], g1[NPT], g2[NPT];
+      const double2 k01 = *reinterpret_cast<const double2 *>(Ss + c * kScal);
+      const double K2 = k01.y;                                   // linear / vah: coefficient of x^2 (or x); feqmod: per-cell renorm
+      const double K3 = (MODEL == M_JONAHLIN) ? Ss[c * kScal + 2] : 0.0;
+      // K0m: term proportional to m^2 (linear: Pi bulk0 m^2; feqmod: (m / T_mod)^2)
+      const double K0m = k01.x * m2;
+      double rn = 0.0;
+      if (MODEL == M_FEQMOD) rn = renorm ? __ldg(renorm + cell_base + c) : K2;
+
+      // phi hoists: a few multiplies per (cell, phi), reused by every slot
+      double q[NPT], pd[NPT], g0[NPT], g1[NPT], g2[NPT], g3[NPT];
 #pragma unroll
       for (int k = 0; k < NPT; k++) {
         const double2 *pr = reinterpret_cast<const double2 *>(Ps + (c * NPT + k) * kRec);
         const double2 v0 = pr[0], v1 = pr[1], v2 = pr[2];
-        q[k] = pT * v0.x;                 // pT * (cos ux + sin uy)/T
-        pd[k] = pT * v0.y;                // pT * (cos dsigma_x + sin dsigma_y)
-        g0[k] = fma(pT2, v1.x, K0m);      // pT^2 Qpp + Pi bulk0 m^2
-        g1[k] = pT * v1.y;
-        g2[k] = pT * v2.x;
+        if (MODEL == M_FEQMOD) {
+          const double tp2 = pT + pT;
+          g1[k] = tp2 * v0.x; g2[k] = tp2 * v0.y; g3[k] = tp2 * v1.x;      // 2 pT w
+          g0[k] = fma(pT2, v1.y, K0m);                                     // pT^2 |w|^2 + (m/T_mod)^2
+          pd[k] = pT * v2.x; q[k] = 0.0;
+        } else {
+          q[k] = pT * v0.x;                 // pT * (cos ux + sin uy)/T
+          pd[k] = pT * v0.y;                // pT * (cos dsigma_x + sin dsigma_y)
+          g0[k] = fma(pT2, v1.x, K0m);      // pT^2 Qpp + (..) m^2
+          g1[k] = pT * v1.y;
+          g2[k] = pT * v2.x;
+          g3[k] = (MODEL == M_VAH) ? pT * v2.y : 0.0;                      // pT (Wx cos + Wy sin)
+        }
       }
-      if (DIM2) {
-#pragma unroll 2
-        for (int j = 0; j < nst; j++) {
-          const double2 *yr = reinterpret_cast<const double2 *>(Ys + (c * nst + j) * kRec);
-          const double2 v0 = yr[0], v1 = yr[1], v2 = yr[2];
+      auto slot = [&](int j, double *accj) {
+        const double2 *yr = reinterpret_cast<const double2 *>(Ys + (c * nst + j) * RY);
+        const double2 v0 = yr[0], v1 = yr[1], v2 = yr[2];
+        if (MODEL == M_FEQMOD) {
+          const double e1 = mT * v0.x, e2 = mT * v0.y, e3 = mT * v1.x, h0 = mT2 * v1.y, cpm = mT * v2.x, w = v2.y;
+#pragma unroll
+          for (int k = 0; k < NPT; k++) {
+            double E2 = h0 + g0[k];
+            E2 = fma(e1, g1[k], E2); E2 = fma(e2, g2[k], E2); E2 = fma(e3, g3[k], E2);   // (E'/T_mod)^2
+            const double x = sqrt_fast(E2);
+            const double pds = fma(w, pd[k], cpm);
+            if (exp_finite(x)) {
+              const double f = rn * occupation(exp_neg(x), sign);
+              accumulate_outflow(accj[k], pds, f, thr);
+            }
+          }
+        } else if (MODEL == M_VAH) {
+          const double2 v3 = yr[3];
+          const double a = mT * v0.x, cpm = mT * v0.y, h0 = mT2 * v1.x, h1 = mT * v1.y, h2 = mT * v2.x, h3 = mT * v2.y;
+          const double hz = mT2 * v3.x, w = v3.y;
+#pragma unroll
+          for (int k = 0; k < NPT; k++) {
+            const double u = a - q[k];                                   // u.p / Lambda
+            const double x = sqrt_fast(fma(u, u, hz));                   // E_a / Lambda
+            const double pds = fma(w, pd[k], cpm);
+            if (exp_finite(x)) {
+              double s = h0 + g0[k];
+              s = fma(g2[k], h2, s);
+              s = fma(-g1[k], h1, s);
+              s = fma(-g3[k], h3, s);
+              s = fma(K2 * u, u, s);
+              const double fa = occupation(exp_neg(x), sign);
+              const double fabar = fma(-sign, fa, 1.0);
+              const double df = clamp_unit(fabar * s, reg_thr);
+              accumulate_outflow(accj[k], pds, fma(fa, df, fa), thr);
+            }
+          }
+        } else {
           const double a = mT * v0.x, cpm = mT * v0.y, h0 = mT2 * v1.x, h1 = mT * v1.y, h2 = mT * v2.x, w = v2.y;
 #pragma unroll
           for (int k = 0; k < NPT; k++) {
             const double x = a - q[k];
             const double pds = fma(w, pd[k], cpm);
-            double s = h0 + g0[k];
-            s = fma(g2[k], h2, s);
-            s = fma(-g1[k], h1, s);
             if (exp_finite(x)) {                           // else exp(x) overflows: f = 0 exactly
-              const double f = distribution<DFM>(x, s, K2, sign, reg_thr);
-              accumulate_outflow(acc[k], pds, f, thr);
+              double s = h0 + g0[k];
+              s = fma(g2[k], h2, s);
+              s = fma(-g1[k], h1, s);
+              const double f = distribution<MODEL>(x, s, K2, K3, sign, reg_thr);
+              accumulate_outflow(accj[k], pds, f, thr);
             }
           }
         }
+      };
+      if (DIM2) {
+#pragma unroll 2
+        for (int j = 0; j < nst; j++) slot(j, acc);
       } else {
 #pragma unroll
-        for (int j = 0; j < NYT; j++) {
-          const double2 *yr = reinterpret_cast<const double2 *>(Ys + (c * NYT + j) * kRec);
-          const double2 v0 = yr[0], v1 = yr[1], v2 = yr[2];
-          const double a = mT * v0.x, cpm = mT * v0.y, h0 = mT2 * v1.x, h1 = mT * v1.y, h2 = mT * v2.x;
-#pragma unroll
-          for (int k = 0; k < NPT; k++) {
-            const double x = a - q[k];
-            const double pds = cpm + pd[k];
-            double s = h0 + g0[k];
-            s = fma(g2[k], h2, s);
-            s = fma(-g1[k], h1, s);
-            if (exp_finite(x)) {
-              const double f = distribution<DFM>(x, s, K2, sign, reg_thr);
-              accumulate_outflow(acc[j * NPT + k], pds, f, thr);
-            }
-          }
-        }
+        for (int j = 0; j < NYT; j++) slot(j, acc + j * NPT);
       }
     }
     __syncthreads();                                   // every warp is done with stage st
@@ -224,15 +260,16 @@ void hot_variant_shape(int variant, int dim2, int *nyt, int *npt, int *ct)
   *nyt = s.nyt; *npt = s.npt; *ct = s.ct;
 }
 
-template <int DFM, int NYT, int NPT, bool DIM2, int MINB>
+template <int MODEL, int NYT, int NPT, bool DIM2, int MINB>
 static cudaError_t launch_one(const HotParams &hp, cudaStream_t st, size_t *smem_out)
 {
   const Layout &L = hp.L;
+  constexpr int RY = (MODEL == M_VAH) ? kRecVah : kRec;
   const int nst = DIM2 ? L.nst : NYT;
-  const size_t stage_doubles = (size_t)L.ct * nst * kRec + (size_t)L.ct * NPT * kRec + (size_t)L.ct * kScal;
+  const size_t stage_doubles = (size_t)L.ct * nst * RY + (size_t)L.ct * NPT * kRec + (size_t)L.ct * kScal;
   const size_t smem = kStages * stage_doubles * 8 + kStages * sizeof(uint64_t);
   if (smem_out) *smem_out = smem;
-  auto kern = cf_vh_kernel<DFM, NYT, NPT, DIM2, MINB>;
+  auto kern = cf_kernel<MODEL, NYT, NPT, DIM2, MINB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t grid = (int64_t)hp.n_groupblocks * L.n_ytiles * L.n_ptiles * hp.n_chunks;
@@ -241,37 +278,43 @@ static cudaError_t launch_one(const HotParams &hp, cudaStream_t st, size_t *smem
   return cudaGetLastError();
 }
 
-template <int DFM>
-static cudaError_t launch_dfm(const HotParams &hp, int variant, cudaStream_t st, size_t *smem_out)
+template <int MODEL>
+static cudaError_t launch_model(const HotParams &hp, int variant, cudaStream_t st, size_t *smem_out)
 {
   if (hp.L.dim2) {
     switch (variant) {
-      case 1: return launch_one<DFM, 1, 4, true, 4>(hp, st, smem_out);
-      case 2: return launch_one<DFM, 1, 6, true, 3>(hp, st, smem_out);
-      case 3: return launch_one<DFM, 1, 8, true, 3>(hp, st, smem_out);
-      case 4: return launch_one<DFM, 1, 2, true, 5>(hp, st, smem_out);
-      case 5: return launch_one<DFM, 1, 12, true, 2>(hp, st, smem_out);
-      case 6: return launch_one<DFM, 1, 4, true, 3>(hp, st, smem_out);
-      case 7: return launch_one<DFM, 1, 1, true, 6>(hp, st, smem_out);
-      default: return launch_one<DFM, 1, 3, true, 4>(hp, st, smem_out);
+      case 1: return launch_one<MODEL, 1, 4, true, 4>(hp, st, smem_out);
+      case 2: return launch_one<MODEL, 1, 6, true, 3>(hp, st, smem_out);
+      case 3: return launch_one<MODEL, 1, 8, true, 3>(hp, st, smem_out);
+      case 4: return launch_one<MODEL, 1, 2, true, 5>(hp, st, smem_out);
+      case 5: return launch_one<MODEL, 1, 12, true, 2>(hp, st, smem_out);
+      case 6: return launch_one<MODEL, 1, 4, true, 3>(hp, st, smem_out);
+      case 7: return launch_one<MODEL, 1, 1, true, 6>(hp, st, smem_out);
+      default: return launch_one<MODEL, 1, 3, true, 4>(hp, st, smem_out);
     }
   }
   switch (variant) {
-    case 1: return launch_one<DFM, 7, 3, false, 3>(hp, st, smem_out);
-    case 2: return launch_one<DFM, 7, 2, false, 4>(hp, st, smem_out);
-    case 3: return launch_one<DFM, 7, 4, false, 3>(hp, st, smem_out);
-    case 4: return launch_one<DFM, 7, 2, false, 5>(hp, st, smem_out);
-    case 5: return launch_one<DFM, 3, 6, false, 3>(hp, st, smem_out);
-    case 6: return launch_one<DFM, 7, 6, false, 2>(hp, st, smem_out);
-    case 7: return launch_one<DFM, 7, 3, false, 4>(hp, st, smem_out);
-    default: return launch_one<DFM, 7, 1, false, 6>(hp, st, smem_out);
+    case 1: return launch_one<MODEL, 7, 3, false, 3>(hp, st, smem_out);
+    case 2: return launch_one<MODEL, 7, 2, false, 4>(hp, st, smem_out);
+    case 3: return launch_one<MODEL, 7, 4, false, 3>(hp, st, smem_out);
+    case 4: return launch_one<MODEL, 7, 2, false, 5>(hp, st, smem_out);
+    case 5: return launch_one<MODEL, 3, 6, false, 3>(hp, st, smem_out);
+    case 6: return launch_one<MODEL, 7, 6, false, 2>(hp, st, smem_out);
+    case 7: return launch_one<MODEL, 7, 3, false, 4>(hp, st, smem_out);
+    default: return launch_one<MODEL, 7, 1, false, 6>(hp, st, smem_out);
   }
 }
 
-cudaError_t launch_hot_vh(const is3d_flags &fl, const HotParams &hp, int variant, cudaStream_t st, size_t *smem_out)
+cudaError_t launch_hot(int model, const HotParams &hp, int variant, cudaStream_t st, size_t *smem_out)
 {
-  if (fl.df_mode == 1) return launch_dfm<1>(hp, variant, st, smem_out);
-  return launch_dfm<2>(hp, variant, st, smem_out);
+  switch (model) {
+    case M_LIN14: return launch_model<M_LIN14>(hp, variant, st, smem_out);
+    case M_LINCE: return launch_model<M_LINCE>(hp, variant, st, smem_out);
+    case M_FEQMOD: return launch_model<M_FEQMOD>(hp, variant, st, smem_out);
+    case M_JONAHLIN: return launch_model<M_JONAHLIN>(hp, variant, st, smem_out);
+    case M_VAH: return launch_model<M_VAH>(hp, variant, st, smem_out);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ FP64 peak probe

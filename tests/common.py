@@ -33,6 +33,9 @@ def surface_columns(recipe, fx):
 def problem_from_recipe(recipe, fx, jonah_with_oracle=True):
     """Inputs for the oracle / the C ABI: (flags, cells, species, grid, df tables, laguerre)."""
     p = recipe["params"]
+    if recipe["generator"] == "vah":
+        fl, cells, sp, g, _ = vah_problem(recipe, fx)
+        return fl, cells, sp, g, None, None
     cols = surface_columns(recipe, fx)
     cells = synthetic.columns_to_cells(cols, 1)
     eos = p.get("hrg_eos", 1)
@@ -55,6 +58,50 @@ def jonah_tables(cells, fx, eos, gla):
     avg = [float("%.15g" % v) for v in cfo.surface_averages(cells)]
     pdg = tables.pdg_table(fx, eos)
     return cfo.jonah_tables(pdg["mass"], pdg["gspin"].astype(float), pdg["sign"].astype(float), avg[0], gla)
+
+
+def vah_cells(cols, fx):
+    """Mode-2 columns -> SoA dict incl. alpha_L, Lambda (readindata.cpp:905-918) and per-cell c0..c4 from the vah tables
+    (bilinear in (Lambda [fm^-1], alpha_L), / hbarC^3; only specification: reference src/cuda/deltafReader.cu:192-277)."""
+    from oracle import cf_oracle as cfo
+    hb = synthetic.HBARC
+    cells = synthetic.columns_to_cells(cols, 2)
+    a = np.asarray(cols)
+    Tf, Pf, PLf = a[:, 13], a[:, 14], a[:, 15]
+    lib = cfo.lib()
+    aL = np.array([lib.cfo_aL_fit(float(x)) for x in PLf / Pf])
+    Lam = np.array([t / (0.5 * al * lib.cfo_R200(float(al))) ** 0.25 for t, al in zip(Tf, aL)])
+    cells["aL"] = aL; cells["Lambda"] = Lam * hb
+    nL, naL = int(fx["df_vah/nL"]), int(fx["df_vah/naL"])
+    Lg = fx["df_vah/L_col"][:nL]; ag = fx["df_vah/aL_col"][::nL]
+    i1 = np.searchsorted(Lg, Lam, side="right"); i2 = np.searchsorted(ag, aL, side="right")
+    assert np.all((i1 >= 1) & (i1 < nL) & (i2 >= 1) & (i2 < naL)), "cell outside the vah table"
+    L1, L2, a1, a2 = Lg[i1 - 1], Lg[i1], ag[i2 - 1], ag[i2]
+    for k in range(5):
+        t = fx["df_vah/c%d" % k].reshape(naL, nL)          # file order: alpha_L outer, Lambda inner
+        f11, f21, f12, f22 = t[i2 - 1, i1 - 1], t[i2 - 1, i1], t[i2, i1 - 1], t[i2, i1]
+        v = ((f11 * (L2 - Lam) + f21 * (Lam - L1)) * (a2 - aL) + (f12 * (L2 - Lam) + f22 * (Lam - L1)) * (aL - a1)) / ((a2 - a1) * (L2 - L1))
+        cells["c%d" % k] = v / (hb * hb * hb)
+    return cells
+
+
+def vah_columns(n_cells, seed, dimension):
+    cols = synthetic.surface_vah(n_cells, seed)
+    if dimension == 2:
+        cols[:, 3] = 0.0; cols[:, 7] = 0.0; cols[:, 11] = 0.0       # eta, dsigma_eta, u^eta
+    return cols
+
+
+def vah_problem(recipe, fx):
+    p = recipe["params"]
+    cols = vah_columns(recipe["n_cells"], recipe["seed"], p["dimension"])
+    cells = vah_cells(cols, fx)
+    sp = tables.species(fx, p.get("hrg_eos", 1), recipe["chosen"])
+    g = tables.grid(fx)
+    fl = tables.flags(df_mode=p.get("df_mode", 1), dimension=p["dimension"], include_bulk=p.get("include_bulk_deltaf", 1),
+                      include_shear=p.get("include_shear_deltaf", 1), regulate_deltaf=p.get("regulate_deltaf", 1), outflow=p.get("outflow", 1))
+    fl["mode"] = 2
+    return fl, cells, sp, g, cols
 
 
 def compare(got, ref, tol=REL_TOL):

@@ -39,6 +39,8 @@ CASES = {
     "s2_ideal": ("vh", dict(three_d=False, viscous=False), 30, 1002, "chosen_pikp",
                  dict(hrg_eos=1, dimension=2, df_mode=1, include_bulk_deltaf=0, include_shear_deltaf=0), "kernel"),
     "s3_heavy_df1": ("vh", dict(three_d=True), 60, 1003, HEAVY, dict(hrg_eos=1, dimension=3, df_mode=1), "kernel"),
+    "vah_3d": ("vah", {}, 120, 1005, "chosen_pikp", dict(hrg_eos=1, dimension=3, df_mode=1, mode=2), "vah"),
+    "vah_2d": ("vah", {}, 16, 1006, "chosen_pikp", dict(hrg_eos=1, dimension=2, df_mode=1, mode=2), "vah"),
     "s3_noreg_df1": ("vh", dict(three_d=True), 100, 1003, "chosen_pikp",
                      dict(hrg_eos=1, dimension=3, df_mode=1, regulate_deltaf=0, outflow=0), "kernel"),
 }
@@ -61,9 +63,19 @@ def main():
     for name, (gen, kw, n, seed, chosen, params, what) in CASES.items():
         if only and name not in only:
             continue
-        cols = surface(name, fx)
         wd = tempfile.mkdtemp(prefix="is3d_golden_")
-        workdir.materialize(wd, surface_columns=cols, chosen=chosen, fixture=fx, operation=1, mode=1, **params)
+        if gen == "vah":
+            # the reference's anisotropic kernel is called directly; per-cell c0..c4 (no reader exists in src/cpp) come
+            # from the test-suite's restatement of the only specification (src/cuda/deltafReader.cu:192-277)
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from common import vah_cells, vah_columns
+            cols = vah_columns(n, seed, params["dimension"])
+            cells = vah_cells(cols, fx)
+            workdir.materialize(wd, surface_columns=cols, chosen=chosen, fixture=fx, operation=1, **params)
+            np.concatenate([cells["c%d" % k] for k in range(5)]).tofile(os.path.join(wd, "input", "vah_coefficients.bin"))
+        else:
+            cols = surface(name, fx)
+            workdir.materialize(wd, surface_columns=cols, chosen=chosen, fixture=fx, operation=1, mode=1, **params)
         dN, info = cfo.run_reference(wd, what=what)
         rec = dict(dN=dN, mcid=np.array(info["mcid"], dtype=np.int64), breakdown=np.array(info["breakdown"]),
                    recipe=np.array(json.dumps(dict(generator=gen, kwargs=kw, n_cells=n, seed=seed, params=params, what=what,

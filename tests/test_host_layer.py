@@ -186,3 +186,17 @@ def test_table_builders_match_oracle(fx):
     for k in ("jonah_x", "jonah_lambda2", "jonah_z"):
         assert np.array_equal(mine[k], ref[k]), k
     assert mine["bulkPi_over_Peq_max"] == ref["bulkPi_over_Peq_max"]
+
+
+def test_surface_reader_mode2_and_vah_coefficients(fx):
+    """anisotropic-hydro surface (31 columns): alpha_L / Lambda inference and the (Lambda, alpha_L) coefficient lookup"""
+    from common import vah_cells
+    cols = synthetic.surface_vah(64, 1005)
+    with tempfile.TemporaryDirectory() as wd:
+        workdir.materialize(wd, surface_columns=cols, fixture=fx, hrg_eos=1, mode=2, vah=True)
+        d = host_dump(wd)
+    ref = vah_cells(cols, fx)
+    for k in ("tau", "ux", "un", "pitt", "pitn", "pinn", "pixx", "Wx", "Wy", "bulkPi"):
+        assert np.array_equal(d[k], ref[k]), k
+    for k in ("aL", "Lambda", "c0", "c1", "c2", "c3", "c4"):
+        assert np.allclose(d[k], ref[k], rtol=1e-12, atol=0), k

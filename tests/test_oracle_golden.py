@@ -11,13 +11,18 @@ def test_oracle_matches_reference_vector(name, fx):
     gold = load_golden(name)
     fl, cells, sp, g, tab, gla = problem_from_recipe(gold["recipe"], fx)
     assert list(sp["mcid"]) == list(gold["mcid"])                      # species order: integer bookkeeping, exact
-    dN, skipped, breakdown = cfo.smooth(fl, cells, sp, g, tab, gla)
+    vah = gold["recipe"]["generator"] == "vah"
+    dN, skipped, breakdown = cfo.smooth(fl, cells, sp, g, tab, gla, vah=vah)
     assert skipped == 0
     assert breakdown == int(gold["breakdown"])
     rep = compare(dN, gold["dN"], tol=1e-13)
     assert rep["ok"], rep
-    # the restatement keeps the reference's operation order: in practice it is bit-identical
-    assert np.array_equal(dN, gold["dN"]), rep
+    if not vah:
+        # the restatement keeps the reference's operation order: in practice it is bit-identical
+        assert np.array_equal(dN, gold["dN"]), rep
+    else:
+        # alpha_L / Lambda are re-derived by the reference's own reader (explicit powers vs Horner: 1-ulp inputs)
+        assert rep["max_rel"] < 1e-12, rep
 
 
 def test_toy_cell_closed_form(fx):
