@@ -395,7 +395,7 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
   CU_CHECK(cudaEventRecord(ev[3], st));
 
   // ---- reduce chunks, add into the result
-  CU_CHECK(launch_reduce(hp.partial, n_chunks * reduce_sets, n_bins, dN_dev, st));
+  CU_CHECK(launch_reduce(hp.partial, n_chunks * reduce_sets, n_bins, dim2 ? n_bins / gr->n_y : n_bins, dN_dev, st));
   stt.gpu_launches++;
   CU_CHECK(cudaEventRecord(ev[4], st));
 

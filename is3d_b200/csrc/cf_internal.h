@@ -80,7 +80,7 @@ cudaError_t launch_prepare_feqmod(const is3d_flags &fl, const RawCells &cells, c
 cudaError_t launch_prepare_vah(const is3d_flags &fl, const RawCells &cells, const PrepTables &tab, const Layout &L,
                                double *Y, double *P, double *S, PrepCounters *counters, cudaStream_t st);
 cudaError_t launch_hot(int model, const HotParams &hp, int variant, cudaStream_t st, size_t *smem_out);
-cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, double *out, cudaStream_t st);
+cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, int64_t n_active, double *out, cudaStream_t st);
 cudaError_t launch_fp64_peak(double *sink, int iters, cudaStream_t st, int *blocks, int *threads, long long *dfma_per_thread);
 void hot_variant_shape(int variant, int dim2, int *nyt, int *npt, int *ct);
 

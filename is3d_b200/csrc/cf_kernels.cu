@@ -229,19 +229,20 @@ cf_kernel(const HotParams hp)
 }
 
 // ------------------------------------------------------------------------------------------------ reduce
-__global__ void reduce_kernel(const double *__restrict__ partial, int n_chunks, int64_t n_bins, double *__restrict__ out)
+// n_active <= n_bins: only the bins the hot kernel writes (2+1D fills the iy = 0 plane, the first n_bins / n_y entries)
+__global__ void reduce_kernel(const double *__restrict__ partial, int n_chunks, int64_t n_bins, int64_t n_active, double *__restrict__ out)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_bins) return;
+  if (i >= n_active) return;
   double s = 0.0;
   for (int c = 0; c < n_chunks; c++) s += partial[(int64_t)c * n_bins + i];
   out[i] += s;
 }
 
-cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, double *out, cudaStream_t st)
+cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, int64_t n_active, double *out, cudaStream_t st)
 {
-  if (n_bins == 0) return cudaSuccess;
-  reduce_kernel<<<(unsigned)((n_bins + 255) / 256), 256, 0, st>>>(partial, n_chunks, n_bins, out);
+  if (n_active == 0) return cudaSuccess;
+  reduce_kernel<<<(unsigned)((n_active + 255) / 256), 256, 0, st>>>(partial, n_chunks, n_bins, n_active, out);
   return cudaGetLastError();
 }
 

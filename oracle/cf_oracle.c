@@ -253,7 +253,7 @@ static int grid_dims(const cfo_flags *fl, const cfo_grid *g, int *y_pts, int *et
 
 /* ---------------------------------------------------------------- a1: linear delta-f kernel, :28-393 */
 int64_t cfo_smooth_vh(const cfo_flags *fl, const cfo_cells *c, const cfo_species *sp, const cfo_grid *g,
-                      const cfo_df_tables *tab, double *dN)
+                      const cfo_df_tables *tab, double *dN, double *dN_abs)
 {
   if (fl->df_mode != 1 && fl->df_mode != 2) return -1;
   if (fl->include_baryon) return -2;                    /* bilinear (T, muB) lookup: reference indexes out of bounds (R8) */
@@ -302,7 +302,7 @@ int64_t cfo_smooth_vh(const cfo_flags *fl, const cfo_cells *c, const cfo_species
           double px = pT * cosphi[iphip], py = pT * sinphi[iphip];
           for (int iy = 0; iy < y_pts; iy++) {
             double y = (fl->dimension == 2) ? 0.0 : g->y[iy];
-            double sum = 0.0;
+            double sum = 0.0, sum_abs = 0.0;
             for (int ieta = 0; ieta < eta_pts; ieta++) {
               double eta = (fl->dimension == 2) ? g->eta[ieta] : s->eta;
               double eta_weight = (fl->dimension == 2) ? g->eta_weight[ieta] : 1.0;
@@ -313,6 +313,7 @@ int64_t cfo_smooth_vh(const cfo_flags *fl, const cfo_cells *c, const cfo_species
               if (fl->outflow && pdotdsigma <= 0.0) continue;
               double pdotu = pt * s->ut - px * s->ux - py * s->uy - tau2_pn * s->un;
               double feq = 1.0 / (exp(pdotu / s->T - chem) + sign);
+              double mag = 0.0;           /* |df_shear| + |df_bulk| + |df_diff| built from absolute values of every term */
               double feqbar = 1.0 - sign * feq;
               double pimunu_pmu_pnu = s->pitt * pt * pt + s->pixx * px * px + s->piyy * py * py + s->pinn * tau2_pn * tau2_pn
                 + 2.0 * (-(s->pitx * px + s->pity * py) * pt + s->pixy * px * py + tau2_pn * (s->pixn * px + s->piyn * py - s->pitn * pt));
@@ -323,18 +324,28 @@ int64_t cfo_smooth_vh(const cfo_flags *fl, const cfo_cells *c, const cfo_species
                 double df_bulk = (s->bulk0_coeff * mass2 + (s->bulk1_coeff * baryon + s->bulk2_coeff * pdotu) * pdotu) * s->bulkPi;
                 double df_diff = (s->df.c3 * baryon + s->df.c4 * pdotu) * Vmu_pmu;
                 df = feqbar * (df_shear + df_bulk + df_diff);
+                mag = fabs(s->shear_coeff) * (fabs(s->pitt) * pt * pt + fabs(s->pixx) * px * px + fabs(s->piyy) * py * py + fabs(s->pinn) * tau2_pn * tau2_pn
+                      + 2.0 * ((fabs(s->pitx * px) + fabs(s->pity * py)) * pt + fabs(s->pixy * px * py) + fabs(tau2_pn) * (fabs(s->pixn * px) + fabs(s->piyn * py) + fabs(s->pitn) * pt)))
+                      + (fabs(s->bulk0_coeff) * mass2 + fabs(s->bulk2_coeff) * pdotu * pdotu) * fabs(s->bulkPi) + fabs(df_diff);
               } else {
                 double df_shear = s->shear_coeff * pimunu_pmu_pnu / pdotu;
                 double df_bulk = (s->bulk0_coeff * pdotu + s->bulk1_coeff * baryon + s->bulk2_coeff * (pdotu - mass2 / pdotu)) * s->bulkPi;
                 double df_diff = (s->baryon_enthalpy_ratio - baryon / pdotu) * Vmu_pmu / s->df.betaV;
                 df = feqbar * (df_shear + df_bulk + df_diff);
+                mag = fabs(s->shear_coeff) / pdotu * (fabs(s->pitt) * pt * pt + fabs(s->pixx) * px * px + fabs(s->piyy) * py * py + fabs(s->pinn) * tau2_pn * tau2_pn
+                      + 2.0 * ((fabs(s->pitx * px) + fabs(s->pity * py)) * pt + fabs(s->pixy * px * py) + fabs(tau2_pn) * (fabs(s->pixn * px) + fabs(s->piyn * py) + fabs(s->pitn) * pt)))
+                      + (fabs(s->bulk0_coeff) * pdotu + fabs(s->bulk2_coeff) * (pdotu + mass2 / pdotu)) * fabs(s->bulkPi) + fabs(df_diff);
               }
-              if (fl->regulate_deltaf) df = fmax(-1.0, fmin(df, 1.0));
+              int clamped = 0;
+              if (fl->regulate_deltaf) { clamped = (df <= -1.0 || df >= 1.0); df = fmax(-1.0, fmin(df, 1.0)); }
               double f = feq * (1.0 + df);
               sum += (pdotdsigma * f);
+              /* magnitude of the terms that make up f: its rounding noise is a few ulp of this, however small f itself is */
+              sum_abs += fabs(pdotdsigma) * feq * (1.0 + (clamped ? 1.0 : fabs(feqbar) * mag));
             }
             int64_t iS3D = (int64_t)ipart + (int64_t)npart * ((int64_t)ipT + (int64_t)npT * ((int64_t)iphip + (int64_t)nphi * (int64_t)iy));
             dN[iS3D] += (prefactor * degeneracy * sum);
+            if (dN_abs) dN_abs[iS3D] += (prefactor * degeneracy * sum_abs);
           }
         }
       }

@@ -78,9 +78,11 @@ void cfo_surface_averages(const cfo_cells *c, double *out5);
 
 /* EmissionFunctionArray::calculate_dN_pTdpTdphidy, emissionfunction_smooth_kernels.cpp:28-393 (df_mode 1,2).
  * dN is [n_y_tab][n_phi][n_pT][n_species] (species fastest) and is ADDED into.  Returns #cells skipped (u.dsigma<=0)
- * or a negative error code. */
+ * or a negative error code.
+ * dN_abs (optional, may be NULL) receives, per bin, the same sum with every term of delta-f replaced by its absolute value:
+ * the bin's floating-point noise floor is a few ulp of dN_abs, which matters where 1 + df nearly cancels. */
 int64_t cfo_smooth_vh(const cfo_flags *fl, const cfo_cells *c, const cfo_species *sp, const cfo_grid *g,
-                      const cfo_df_tables *tab, double *dN);
+                      const cfo_df_tables *tab, double *dN, double *dN_abs);
 
 /* EmissionFunctionArray::calculate_dN_ptdptdphidy_feqmod, :396-996 (df_mode 3,4).  *breakdown gets the cell count. */
 int64_t cfo_smooth_feqmod(const cfo_flags *fl, const cfo_cells *c, const cfo_species *sp, const cfo_grid *g,

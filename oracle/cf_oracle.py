@@ -156,8 +156,10 @@ def jonah_tables(mass, degeneracy, sign, T_avg, gla):
     return dict(jonah_x=x, jonah_lambda2=l2, jonah_z=z, bulkPi_over_Peq_max=mx)
 
 
-def smooth(flags, cells, species, grid, tables=None, laguerre=None, vah=False):
-    """Run the matching oracle kernel; returns (dN flat [y][phi][pT][species], skipped, breakdown)."""
+def smooth(flags, cells, species, grid, tables=None, laguerre=None, vah=False, conditioning=None):
+    """Run the matching oracle kernel; returns (dN flat [y][phi][pT][species], skipped, breakdown).
+
+    conditioning: optional zero-initialised array (df_mode 1, 2 only) that receives the per-bin magnitude sum dN_abs."""
     keep = _Keep()
     dN = np.zeros(n_bins(species, grid))
     fl = _flags(flags); c = _cells(keep, cells); sp = _species(keep, species); g = _grid(keep, grid)
@@ -166,7 +168,7 @@ def smooth(flags, cells, species, grid, tables=None, laguerre=None, vah=False):
         rc = lib().cfo_smooth_vah(C.byref(fl), C.byref(c), C.byref(sp), C.byref(g), _p(dN))
     elif flags["df_mode"] in (1, 2):
         t = _tables(keep, tables)
-        rc = lib().cfo_smooth_vh(C.byref(fl), C.byref(c), C.byref(sp), C.byref(g), C.byref(t), _p(dN))
+        rc = lib().cfo_smooth_vh(C.byref(fl), C.byref(c), C.byref(sp), C.byref(g), C.byref(t), _p(dN), _p(conditioning) if conditioning is not None else None)
     else:
         t = _tables(keep, tables); la = _laguerre(keep, laguerre)
         rc = lib().cfo_smooth_feqmod(C.byref(fl), C.byref(c), C.byref(sp), C.byref(g), C.byref(t), C.byref(la), _p(dN), C.byref(bd))

@@ -181,9 +181,18 @@ def test_sampled_bins_against_oracle_at_full_species(big, fx):
     cells, dev, sp, g, tab = big
     sub = {k: v[:64] for k, v in cells.items()}
     fl = tables.flags(df_mode=1, dimension=3)
-    ref, _, _ = cfo.smooth(fl, sub, sp, g, tab, None)
+    cond = np.zeros(305 * 32 * 24 * 21)
+    ref, _, _ = cfo.smooth(fl, sub, sp, g, tab, None, conditioning=cond)
     dN, _ = api.smooth_spectra(fl, sub, sp, g, tab, None)
-    rep = compare(dN, ref)
+    plain = compare(dN, ref)
+    # a handful of the 4.9 M bins are dominated by one cell whose 1 + df nearly cancels: there the reference's own value
+    # is only good to ~1e-9; everywhere else the plain 1e-10 bar holds (see common.compare)
+    nz = ref != 0
+    rel = np.abs(dN[nz] - ref[nz]) / ref[nz]
+    assert (rel > REL_TOL).sum() <= 20 and plain["max_rel"] < 1e-8 and plain["zeros_match"], plain
+    ill = cond[nz][rel > REL_TOL] / ref[nz][rel > REL_TOL]
+    assert np.all(ill > 1e3), ill                                     # every offender is ill-conditioned by > 1000
+    rep = compare(dN, ref, conditioning=cond)
     assert rep["ok"], rep
 
 
