@@ -84,7 +84,7 @@ typedef struct {
   int32_t memory;            /* 0: surface arrays and dN live in host memory; 1: they are device pointers on the current device */
   void *stream;              /* cudaStream_t to launch on (NULL = default stream) */
   int32_t n_chunks;          /* cell-range split used for load balance; 0 = choose */
-  int32_t tile_variant;      /* kernel register-tile variant; 0 = default */
+  int32_t tile_variant;      /* kernel register-tile variant: 0 = tuned default for the model, k = 1..16 selects table entry k - 1 */
   int32_t reserved[4];
 } is3d_options;
 

@@ -202,14 +202,18 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
   const bool dim2 = (fl->dimension == 2);
   const int64_t n_bins = (int64_t)sp->n * gr->n_pT * gr->n_phi * gr->n_y;
 
+  const bool dim2_early = (fl->dimension == 2);
   // ---- layout
   Layout L; memset(&L, 0, sizeof(L));
   L.n_species = sp->n; L.n_pT = gr->n_pT; L.n_phi = gr->n_phi; L.n_y_out = gr->n_y;
   L.dim2 = dim2 ? 1 : 0;
   L.n_slots = dim2 ? gr->n_eta : gr->n_y;
   L.rec_y = vah ? kRecVah : kRec;
-  int variant = opt.tile_variant;
-  if (variant < 0 || variant > 7) variant = 0;
+  // tile_variant: 0 = model default (tuned on B200, see profiles/), k > 0 = table entry k - 1 (tuning / tests)
+  int variant;
+  if (opt.tile_variant >= 1 && opt.tile_variant <= 16) variant = opt.tile_variant - 1;
+  else if (dim2_early) variant = 12;
+  else variant = (model == M_FEQMOD || model == M_VAH) ? 12 : 11;
   int nyt, npt, ct;
   hot_variant_shape(variant, L.dim2, &nyt, &npt, &ct);
   L.nst = dim2 ? L.n_slots : nyt;

@@ -103,6 +103,32 @@ __device__ __forceinline__ double exp_neg(double x)
   return a;
 }
 
+// Staged form for groups of evaluations (lets the scheduler interleave the members' dependency chains):
+//   exp_neg_poly: mantissa polynomial p and binary exponent n with e^{-x} = p 2^n;  exp_neg_fast: exponent insertion;
+//   exp_neg_is_rare / exp_neg_rare: the sub-normal case, tested once per group.
+__device__ __forceinline__ void exp_neg_poly(double x, double &p_out, int &n_out)
+{
+  const double MAGIC = kExpR[1];
+  double fn = fma(x, kExpR[0], MAGIC);
+  n_out = __double2loint(fn);
+  double nf = fn - MAGIC;
+  double r = fma(nf, kExpR[2], -x);
+  r = fma(nf, kExpR[3], r);
+  double p = kExpC[0];
+#pragma unroll
+  for (int k = 1; k < 10; k++) p = fma(p, r, kExpC[k]);
+  p = fma(p, r, 1.0);
+  p_out = fma(p, r, 1.0);
+}
+__device__ __forceinline__ double exp_neg_fast(double p, int n)
+{ return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p)); }
+__device__ __forceinline__ bool exp_neg_is_rare(int n) { return (unsigned)(n + 1021) > 2044u; }
+__device__ __forceinline__ double exp_neg_rare(double p, int n)
+{
+  const int n1 = n >> 1, n2 = n - n1;
+  return (p * __hiloint2double((n1 + 1023) << 20, 0)) * __hiloint2double((n2 + 1023) << 20, 0);
+}
+
 // true when the reference's exp(x) stays finite, i.e. x <= ln(DBL_MAX) = 0x40862E42FEFA39EF; integer compare on
 // the ALU pipe (negative x has the sign bit set and passes).
 __device__ __forceinline__ bool exp_finite(double x)

@@ -37,7 +37,58 @@ __device__ __forceinline__ double distribution(double x, double s, double K2, do
   return fma(feq, df, feq);
 }
 
-template <int MODEL, int NYT, int NPT, bool DIM2, int MINB>
+// SB: evaluations are grouped SB slots x NPT phi points per divergent region (0: one region per evaluation).  Grouping
+// lets the scheduler interleave the independent exp / reciprocal chains of the group (ILP); the cost is that a group is
+// evaluated as soon as one of its members is alive.
+// e^{-x[i]} for a group of N arguments, staged so that the N polynomial chains interleave and the (rare) sub-normal branch
+// is taken once per group
+template <int N>
+__device__ __forceinline__ void exp_neg_group(const double (&x)[N], double (&a)[N])
+{
+  double p[N]; int n[N];
+  bool rare = false;
+#pragma unroll
+  for (int i = 0; i < N; i++) { exp_neg_poly(x[i], p[i], n[i]); rare |= exp_neg_is_rare(n[i]); }
+#pragma unroll
+  for (int i = 0; i < N; i++) a[i] = exp_neg_fast(p[i], n[i]);
+  if (__builtin_expect(rare, 0)) {
+#pragma unroll
+    for (int i = 0; i < N; i++) if (exp_neg_is_rare(n[i])) a[i] = exp_neg_rare(p[i], n[i]);
+  }
+}
+
+// Same as distribution() for a group of N evaluations, staged so that the N dependency chains can be interleaved and the
+// (rare) sub-normal branch is taken once per group.  pds[i] == 0 marks dead members.
+template <int MODEL, int N>
+__device__ __forceinline__ void distribution_group(const double (&x)[N], const double (&s)[N], double K2, double K3, double sign,
+                                                   int reg_thr, double (&f)[N])
+{
+  double p[N], a[N], dfs[N]; int n[N];
+  bool rare = false;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    exp_neg_poly(x[i], p[i], n[i]);
+    rare |= exp_neg_is_rare(n[i]);
+    if (MODEL == M_LIN14) dfs[i] = fma(K2 * x[i], x[i], s[i]);
+    else dfs[i] = fma(s[i], rcp_fast(x[i]), K2 * x[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) a[i] = exp_neg_fast(p[i], n[i]);
+  if (__builtin_expect(rare, 0)) {
+#pragma unroll
+    for (int i = 0; i < N; i++) if (exp_neg_is_rare(n[i])) a[i] = exp_neg_rare(p[i], n[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const double feq = occupation(a[i], sign);
+    const double feqbar = fma(-sign, feq, 1.0);
+    double df = (MODEL == M_JONAHLIN) ? fma(feqbar, dfs[i], K3) : feqbar * dfs[i];
+    df = clamp_unit(df, reg_thr);
+    f[i] = fma(feq, df, feq);
+  }
+}
+
+template <int MODEL, int NYT, int NPT, bool DIM2, int MINB, int SB>
 __global__ void __launch_bounds__(kMaxWarps * 32, MINB)
 cf_kernel(const HotParams hp)
 {
@@ -148,57 +199,156 @@ cf_kernel(const HotParams hp)
         const double2 v0 = yr[0], v1 = yr[1], v2 = yr[2];
         if (MODEL == M_FEQMOD) {
           const double e1 = mT * v0.x, e2 = mT * v0.y, e3 = mT * v1.x, h0 = mT2 * v1.y, cpm = mT * v2.x, w = v2.y;
+          if (SB == 0) {
 #pragma unroll
-          for (int k = 0; k < NPT; k++) {
-            double E2 = h0 + g0[k];
-            E2 = fma(e1, g1[k], E2); E2 = fma(e2, g2[k], E2); E2 = fma(e3, g3[k], E2);   // (E'/T_mod)^2
-            const double x = sqrt_fast(E2);
-            const double pds = fma(w, pd[k], cpm);
-            if (exp_finite(x)) {
-              const double f = rn * occupation(exp_neg(x), sign);
-              accumulate_outflow(accj[k], pds, f, thr);
+            for (int k = 0; k < NPT; k++) {
+              double E2 = h0 + g0[k];
+              E2 = fma(e1, g1[k], E2); E2 = fma(e2, g2[k], E2); E2 = fma(e3, g3[k], E2);   // (E'/T_mod)^2
+              const double x = sqrt_fast(E2);
+              const double pds = fma(w, pd[k], cpm);
+              if (exp_finite(x)) {
+                const double f = rn * occupation(exp_neg(x), sign);
+                accumulate_outflow(accj[k], pds, f, thr);
+              }
+            }
+          } else {
+            double xv[NPT], pv[NPT], av[NPT]; bool any = false;
+#pragma unroll
+            for (int k = 0; k < NPT; k++) {
+              double E2 = h0 + g0[k];
+              E2 = fma(e1, g1[k], E2); E2 = fma(e2, g2[k], E2); E2 = fma(e3, g3[k], E2);
+              const double x = sqrt_fast(E2);
+              const bool alive = exp_finite(x);
+              any |= alive;
+              xv[k] = alive ? x : 1.0;
+              pv[k] = alive ? fma(w, pd[k], cpm) : 0.0;
+            }
+            if (any) {
+              exp_neg_group<NPT>(xv, av);
+#pragma unroll
+              for (int k = 0; k < NPT; k++) accumulate_outflow(accj[k], pv[k], rn * occupation(av[k], sign), thr);
             }
           }
         } else if (MODEL == M_VAH) {
           const double2 v3 = yr[3];
           const double a = mT * v0.x, cpm = mT * v0.y, h0 = mT2 * v1.x, h1 = mT * v1.y, h2 = mT * v2.x, h3 = mT * v2.y;
           const double hz = mT2 * v3.x, w = v3.y;
+          if (SB == 0) {
 #pragma unroll
-          for (int k = 0; k < NPT; k++) {
-            const double u = a - q[k];                                   // u.p / Lambda
-            const double x = sqrt_fast(fma(u, u, hz));                   // E_a / Lambda
-            const double pds = fma(w, pd[k], cpm);
-            if (exp_finite(x)) {
+            for (int k = 0; k < NPT; k++) {
+              const double u = a - q[k];                                   // u.p / Lambda
+              const double x = sqrt_fast(fma(u, u, hz));                   // E_a / Lambda
+              const double pds = fma(w, pd[k], cpm);
+              if (exp_finite(x)) {
+                double s = h0 + g0[k];
+                s = fma(g2[k], h2, s);
+                s = fma(-g1[k], h1, s);
+                s = fma(-g3[k], h3, s);
+                s = fma(K2 * u, u, s);
+                const double fa = occupation(exp_neg(x), sign);
+                const double fabar = fma(-sign, fa, 1.0);
+                const double df = clamp_unit(fabar * s, reg_thr);
+                accumulate_outflow(accj[k], pds, fma(fa, df, fa), thr);
+              }
+            }
+          } else {
+            double xv[NPT], pv[NPT], sv[NPT], av[NPT]; bool any = false;
+#pragma unroll
+            for (int k = 0; k < NPT; k++) {
+              const double u = a - q[k];
+              const double x = sqrt_fast(fma(u, u, hz));
+              const bool alive = exp_finite(x);
+              any |= alive;
+              xv[k] = alive ? x : 1.0;
+              pv[k] = alive ? fma(w, pd[k], cpm) : 0.0;
               double s = h0 + g0[k];
               s = fma(g2[k], h2, s);
               s = fma(-g1[k], h1, s);
               s = fma(-g3[k], h3, s);
-              s = fma(K2 * u, u, s);
-              const double fa = occupation(exp_neg(x), sign);
-              const double fabar = fma(-sign, fa, 1.0);
-              const double df = clamp_unit(fabar * s, reg_thr);
-              accumulate_outflow(accj[k], pds, fma(fa, df, fa), thr);
+              sv[k] = fma(K2 * u, u, s);
+            }
+            if (any) {
+              exp_neg_group<NPT>(xv, av);
+#pragma unroll
+              for (int k = 0; k < NPT; k++) {
+                const double fa = occupation(av[k], sign);
+                const double fabar = fma(-sign, fa, 1.0);
+                const double df = clamp_unit(fabar * sv[k], reg_thr);
+                accumulate_outflow(accj[k], pv[k], fma(fa, df, fa), thr);
+              }
             }
           }
         } else {
           const double a = mT * v0.x, cpm = mT * v0.y, h0 = mT2 * v1.x, h1 = mT * v1.y, h2 = mT * v2.x, w = v2.y;
+          if (SB == 0) {
 #pragma unroll
-          for (int k = 0; k < NPT; k++) {
-            const double x = a - q[k];
-            const double pds = fma(w, pd[k], cpm);
-            if (exp_finite(x)) {                           // else exp(x) overflows: f = 0 exactly
-              double s = h0 + g0[k];
-              s = fma(g2[k], h2, s);
-              s = fma(-g1[k], h1, s);
-              const double f = distribution<MODEL>(x, s, K2, K3, sign, reg_thr);
-              accumulate_outflow(accj[k], pds, f, thr);
+            for (int k = 0; k < NPT; k++) {
+              const double x = a - q[k];
+              const double pds = fma(w, pd[k], cpm);
+              if (exp_finite(x)) {                           // else exp(x) overflows: f = 0 exactly
+                double s = h0 + g0[k];
+                s = fma(g2[k], h2, s);
+                s = fma(-g1[k], h1, s);
+                const double f = distribution<MODEL>(x, s, K2, K3, sign, reg_thr);
+                accumulate_outflow(accj[k], pds, f, thr);
+              }
+            }
+          } else {
+            double xs[NPT]; bool alive[NPT]; bool any = false;
+#pragma unroll
+            for (int k = 0; k < NPT; k++) { xs[k] = a - q[k]; alive[k] = exp_finite(xs[k]); any |= alive[k]; }
+            if (any) {
+              double xv[NPT], sv[NPT], pv[NPT], fv[NPT];
+#pragma unroll
+              for (int k = 0; k < NPT; k++) {
+                xv[k] = alive[k] ? xs[k] : 1.0;                                // dead members: harmless argument, weight 0
+                pv[k] = alive[k] ? fma(w, pd[k], cpm) : 0.0;
+                double s = h0 + g0[k];
+                s = fma(g2[k], h2, s);
+                sv[k] = fma(-g1[k], h1, s);
+              }
+              distribution_group<MODEL, NPT>(xv, sv, K2, K3, sign, reg_thr, fv);
+#pragma unroll
+              for (int k = 0; k < NPT; k++) accumulate_outflow(accj[k], pv[k], fv[k], thr);
             }
           }
+        }
+      };
+      // two slots x NPT phi points per region (linear models, 3+1D)
+      auto slot_pair = [&](int j, double *accj) {
+        const double2 *y0 = reinterpret_cast<const double2 *>(Ys + (c * nst + j) * RY);
+        const double2 *y1 = y0 + RY / 2;
+        const double2 a0 = y0[0], a1 = y0[1], a2 = y0[2], b0 = y1[0], b1 = y1[1], b2 = y1[2];
+        const double aA = mT * a0.x, cA = mT * a0.y, h0A = mT2 * a1.x, h1A = mT * a1.y, h2A = mT * a2.x, wA = a2.y;
+        const double aB = mT * b0.x, cB = mT * b0.y, h0B = mT2 * b1.x, h1B = mT * b1.y, h2B = mT * b2.x, wB = b2.y;
+        double xA[NPT], xB[NPT]; bool lA[NPT], lB[NPT]; bool any = false;
+#pragma unroll
+        for (int k = 0; k < NPT; k++) {
+          xA[k] = aA - q[k]; xB[k] = aB - q[k];
+          lA[k] = exp_finite(xA[k]); lB[k] = exp_finite(xB[k]); any |= lA[k] | lB[k];
+        }
+        if (any) {
+          double xv[2 * NPT], sv[2 * NPT], pv[2 * NPT], fv[2 * NPT];
+#pragma unroll
+          for (int k = 0; k < NPT; k++) {
+            xv[k] = lA[k] ? xA[k] : 1.0; xv[NPT + k] = lB[k] ? xB[k] : 1.0;
+            pv[k] = lA[k] ? fma(wA, pd[k], cA) : 0.0; pv[NPT + k] = lB[k] ? fma(wB, pd[k], cB) : 0.0;
+            double s0 = h0A + g0[k], s1 = h0B + g0[k];
+            s0 = fma(g2[k], h2A, s0); s1 = fma(g2[k], h2B, s1);
+            sv[k] = fma(-g1[k], h1A, s0); sv[NPT + k] = fma(-g1[k], h1B, s1);
+          }
+          distribution_group<MODEL, 2 * NPT>(xv, sv, K2, K3, sign, reg_thr, fv);
+#pragma unroll
+          for (int k = 0; k < 2 * NPT; k++) accumulate_outflow(accj[k], pv[k], fv[k], thr);
         }
       };
       if (DIM2) {
 #pragma unroll 2
         for (int j = 0; j < nst; j++) slot(j, acc);
+      } else if (SB == 2 && MODEL != M_FEQMOD && MODEL != M_VAH) {
+#pragma unroll
+        for (int j = 0; j + 1 < NYT; j += 2) slot_pair(j, acc + j * NPT);
+        if (NYT & 1) slot(NYT - 1, acc + (NYT - 1) * NPT);
       } else {
 #pragma unroll
         for (int j = 0; j < NYT; j++) slot(j, acc + j * NPT);
@@ -247,12 +397,17 @@ cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, i
 }
 
 // ------------------------------------------------------------------------------------------------ dispatch
-// Register-tile variants: (slots per tile, phi points per tile, cells per TMA tile, min blocks per SM).
+// Register-tile variants: (slots per tile, phi points per tile, cells per TMA tile, min blocks per SM, grouping SB).
 // Variant 0 is the default; the others exist for tuning (is3d_options.tile_variant, bench.py --variant).
-struct Shape { int nyt, npt, ct, minb; };
-static const Shape kShapes3D[] = {{7, 1, 16, 6}, {7, 3, 16, 3}, {7, 2, 16, 4}, {7, 4, 16, 3}, {7, 2, 16, 5}, {3, 6, 16, 3}, {7, 6, 16, 2}, {7, 3, 16, 4}};
-static const Shape kShapes2D[] = {{1, 3, 1, 4}, {1, 4, 1, 4}, {1, 6, 1, 3}, {1, 8, 1, 3}, {1, 2, 1, 5}, {1, 12, 1, 2}, {1, 4, 1, 3}, {1, 1, 1, 6}};
-constexpr int kNumVariants = 8;
+// Variants >= 8 are compiled for the 14-moment model only (tuning sweep) and fall back to variant 0 elsewhere.
+struct Shape { int nyt, npt, ct, minb, sb; };
+static const Shape kShapes3D[] = {
+  {7, 1, 16, 6, 0}, {7, 3, 16, 3, 0}, {7, 2, 16, 4, 0}, {7, 4, 16, 3, 0}, {7, 2, 16, 5, 0}, {3, 6, 16, 3, 0}, {7, 6, 16, 2, 0}, {7, 3, 16, 4, 0},
+  {7, 1, 16, 6, 2}, {7, 2, 16, 4, 1}, {7, 2, 16, 5, 1}, {7, 3, 16, 4, 1}, {7, 3, 16, 3, 1}, {7, 2, 16, 4, 2}, {7, 2, 16, 6, 1}, {7, 1, 16, 5, 2}};
+static const Shape kShapes2D[] = {
+  {1, 3, 1, 4, 0}, {1, 4, 1, 4, 0}, {1, 6, 1, 3, 0}, {1, 8, 1, 3, 0}, {1, 2, 1, 5, 0}, {1, 12, 1, 2, 0}, {1, 4, 1, 3, 0}, {1, 1, 1, 6, 0},
+  {1, 2, 1, 6, 1}, {1, 3, 1, 4, 1}, {1, 4, 1, 4, 1}, {1, 4, 1, 3, 1}, {1, 6, 1, 3, 1}, {1, 8, 1, 3, 1}, {1, 3, 1, 5, 1}, {1, 2, 1, 5, 1}};
+constexpr int kNumVariants = 16;
 
 void hot_variant_shape(int variant, int dim2, int *nyt, int *npt, int *ct)
 {
@@ -261,7 +416,7 @@ void hot_variant_shape(int variant, int dim2, int *nyt, int *npt, int *ct)
   *nyt = s.nyt; *npt = s.npt; *ct = s.ct;
 }
 
-template <int MODEL, int NYT, int NPT, bool DIM2, int MINB>
+template <int MODEL, int NYT, int NPT, bool DIM2, int MINB, int SB>
 static cudaError_t launch_one(const HotParams &hp, cudaStream_t st, size_t *smem_out)
 {
   const Layout &L = hp.L;
@@ -270,7 +425,7 @@ static cudaError_t launch_one(const HotParams &hp, cudaStream_t st, size_t *smem
   const size_t stage_doubles = (size_t)L.ct * nst * RY + (size_t)L.ct * NPT * kRec + (size_t)L.ct * kScal;
   const size_t smem = kStages * stage_doubles * 8 + kStages * sizeof(uint64_t);
   if (smem_out) *smem_out = smem;
-  auto kern = cf_kernel<MODEL, NYT, NPT, DIM2, MINB>;
+  auto kern = cf_kernel<MODEL, NYT, NPT, DIM2, MINB, SB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t grid = (int64_t)hp.n_groupblocks * L.n_ytiles * L.n_ptiles * hp.n_chunks;
@@ -282,28 +437,57 @@ static cudaError_t launch_one(const HotParams &hp, cudaStream_t st, size_t *smem
 template <int MODEL>
 static cudaError_t launch_model(const HotParams &hp, int variant, cudaStream_t st, size_t *smem_out)
 {
+  constexpr bool TUNE = true;
   if (hp.L.dim2) {
     switch (variant) {
-      case 1: return launch_one<MODEL, 1, 4, true, 4>(hp, st, smem_out);
-      case 2: return launch_one<MODEL, 1, 6, true, 3>(hp, st, smem_out);
-      case 3: return launch_one<MODEL, 1, 8, true, 3>(hp, st, smem_out);
-      case 4: return launch_one<MODEL, 1, 2, true, 5>(hp, st, smem_out);
-      case 5: return launch_one<MODEL, 1, 12, true, 2>(hp, st, smem_out);
-      case 6: return launch_one<MODEL, 1, 4, true, 3>(hp, st, smem_out);
-      case 7: return launch_one<MODEL, 1, 1, true, 6>(hp, st, smem_out);
-      default: return launch_one<MODEL, 1, 3, true, 4>(hp, st, smem_out);
+      case 1: return launch_one<MODEL, 1, 4, true, 4, 0>(hp, st, smem_out);
+      case 2: return launch_one<MODEL, 1, 6, true, 3, 0>(hp, st, smem_out);
+      case 3: return launch_one<MODEL, 1, 8, true, 3, 0>(hp, st, smem_out);
+      case 4: return launch_one<MODEL, 1, 2, true, 5, 0>(hp, st, smem_out);
+      case 5: return launch_one<MODEL, 1, 12, true, 2, 0>(hp, st, smem_out);
+      case 6: return launch_one<MODEL, 1, 4, true, 3, 0>(hp, st, smem_out);
+      case 7: return launch_one<MODEL, 1, 1, true, 6, 0>(hp, st, smem_out);
+      default: break;
     }
+    if constexpr (TUNE) {
+      switch (variant) {
+        case 8: return launch_one<MODEL, 1, 2, true, 6, 1>(hp, st, smem_out);
+        case 9: return launch_one<MODEL, 1, 3, true, 4, 1>(hp, st, smem_out);
+        case 10: return launch_one<MODEL, 1, 4, true, 4, 1>(hp, st, smem_out);
+        case 11: return launch_one<MODEL, 1, 4, true, 3, 1>(hp, st, smem_out);
+        case 12: return launch_one<MODEL, 1, 6, true, 3, 1>(hp, st, smem_out);
+        case 13: return launch_one<MODEL, 1, 8, true, 3, 1>(hp, st, smem_out);
+        case 14: return launch_one<MODEL, 1, 3, true, 5, 1>(hp, st, smem_out);
+        case 15: return launch_one<MODEL, 1, 2, true, 5, 1>(hp, st, smem_out);
+        default: break;
+      }
+    }
+    return launch_one<MODEL, 1, 3, true, 4, 0>(hp, st, smem_out);
   }
   switch (variant) {
-    case 1: return launch_one<MODEL, 7, 3, false, 3>(hp, st, smem_out);
-    case 2: return launch_one<MODEL, 7, 2, false, 4>(hp, st, smem_out);
-    case 3: return launch_one<MODEL, 7, 4, false, 3>(hp, st, smem_out);
-    case 4: return launch_one<MODEL, 7, 2, false, 5>(hp, st, smem_out);
-    case 5: return launch_one<MODEL, 3, 6, false, 3>(hp, st, smem_out);
-    case 6: return launch_one<MODEL, 7, 6, false, 2>(hp, st, smem_out);
-    case 7: return launch_one<MODEL, 7, 3, false, 4>(hp, st, smem_out);
-    default: return launch_one<MODEL, 7, 1, false, 6>(hp, st, smem_out);
+    case 1: return launch_one<MODEL, 7, 3, false, 3, 0>(hp, st, smem_out);
+    case 2: return launch_one<MODEL, 7, 2, false, 4, 0>(hp, st, smem_out);
+    case 3: return launch_one<MODEL, 7, 4, false, 3, 0>(hp, st, smem_out);
+    case 4: return launch_one<MODEL, 7, 2, false, 5, 0>(hp, st, smem_out);
+    case 5: return launch_one<MODEL, 3, 6, false, 3, 0>(hp, st, smem_out);
+    case 6: return launch_one<MODEL, 7, 6, false, 2, 0>(hp, st, smem_out);
+    case 7: return launch_one<MODEL, 7, 3, false, 4, 0>(hp, st, smem_out);
+    default: break;
   }
+  if constexpr (TUNE) {
+    switch (variant) {
+      case 8: return launch_one<MODEL, 7, 1, false, 6, 2>(hp, st, smem_out);
+      case 9: return launch_one<MODEL, 7, 2, false, 4, 1>(hp, st, smem_out);
+      case 10: return launch_one<MODEL, 7, 2, false, 5, 1>(hp, st, smem_out);
+      case 11: return launch_one<MODEL, 7, 3, false, 4, 1>(hp, st, smem_out);
+      case 12: return launch_one<MODEL, 7, 3, false, 3, 1>(hp, st, smem_out);
+      case 13: return launch_one<MODEL, 7, 2, false, 4, 2>(hp, st, smem_out);
+      case 14: return launch_one<MODEL, 7, 2, false, 6, 1>(hp, st, smem_out);
+      case 15: return launch_one<MODEL, 7, 1, false, 5, 2>(hp, st, smem_out);
+      default: break;
+    }
+  }
+  return launch_one<MODEL, 7, 1, false, 6, 0>(hp, st, smem_out);
 }
 
 cudaError_t launch_hot(int model, const HotParams &hp, int variant, cudaStream_t st, size_t *smem_out)

@@ -42,7 +42,7 @@ def parity():
         fl = tables.flags(df_mode=dfm, dimension=dim, **extra)
         ref, sk, bd = cfo.smooth(fl, cells, sp, g, tab, gla)
         for variant in (0, 2, 5):
-            got, st = api.smooth_spectra(fl, cells, sp, g, tab, gla, tile_variant=variant)
+            got, st = api.smooth_spectra(fl, cells, sp, g, tab, gla, tile_variant=variant + 1)
             e = relerr(got, ref)
             good = e["max"] <= 1e-10 and e["zeros_equal"] and st["cells_skipped_udsigma"] == sk
             ok &= good
@@ -53,51 +53,49 @@ def parity():
     return ok
 
 
-def sweep(n_cells, n_species, variants, dims=(3,)):
+def sweep(n_cells, n_species, variants, dims=(3,), models=("lin14", "lince")):
     import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
     fx = tables.load_fixture()
     g = tables.grid(fx)
     sp_all = tables.species(fx, 1, "chosen_urqmd")
     sp = {k: v[:n_species] for k, v in sp_all.items()}
-    tab = tables.df_tables(fx, 1)
+    tab = tables.df_tables(fx, 1); gla = tables.laguerre(fx)
     peak, ms = api.measure_fp64_peak()
     print("FP64_PEAK %.2f TFLOP/s (%.2f ms)" % (peak, ms), flush=True)
-    import subprocess, statistics
-    mon = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.active", "--format=csv,noheader,nounits", "-lms", "100"],
-                           stdout=open("/tmp/clk.csv", "w"))
-    def clocks(tag):
-        try:
-            rows = [l.split(",") for l in open("/tmp/clk.csv").read().strip().splitlines()]
-            cl = [float(r[0]) for r in rows[-15:]]; pw = [float(r[1]) for r in rows[-15:]]
-            print("CLOCKS %s last1.5s: sm_mhz median %.0f min %.0f power max %.0f reasons %s" % (tag, statistics.median(cl), min(cl), max(pw), rows[-1][2].strip()), flush=True)
-        except Exception as e:
-            print("CLOCKS", tag, "n/a", e)
-    sus = api.measure_fp64_sustained(3.0)
-    clocks("fp64_sustained")
-    print("FP64_SUSTAINED %.2f TFLOP/s over 3 s" % sus, flush=True)
+    W = {"lin14": 85, "lince": 87, "mike": 140, "jonah": 140, "vah": 94}
     out = []
     for dim in dims:
         nc = n_cells if dim == 3 else max(n_cells // 10, 100)
-        cols = synthetic.surface_vh(nc, 1003, three_d=(dim == 3))
-        cells = synthetic.columns_to_cells(cols, 1)
-        dev = {k: torch.tensor(v, device="cuda") for k, v in cells.items()}
-        for dfm in (1, 2):
-            fl = tables.flags(df_mode=dfm, dimension=dim)
+        for model in models:
+            if model == "vah":
+                from common import vah_cells, vah_columns
+                cells = vah_cells(vah_columns(nc, 1005, dim), fx)
+                fl = tables.flags(df_mode=1, dimension=dim); fl["mode"] = 2
+                t2 = None
+            else:
+                cols = synthetic.surface_vh(nc, 1003, three_d=(dim == 3))
+                cells = synthetic.columns_to_cells(cols, 1)
+                dfm = {"lin14": 1, "lince": 2, "mike": 3, "jonah": 4}[model]
+                fl = tables.flags(df_mode=dfm, dimension=dim)
+                t2 = dict(tab)
+                if dfm == 4:
+                    pdg = tables.pdg_table(fx, 1); avg = api.surface_averages(cells)
+                    t2.update(api.jonah_tables(pdg["mass"], pdg["gspin"].astype(float), pdg["sign"].astype(float), avg[0], gla))
+            dev = {k: torch.tensor(v, device="cuda") for k, v in cells.items() if v is not None}
             for v in variants:
                 best = None
                 for rep in range(2):
-                    res, st = api.smooth_spectra(fl, dev, sp, g, tab, None, memory="device", tile_variant=v)
+                    res, st = api.smooth_spectra(fl, dev, sp, g, t2, gla, memory="device", tile_variant=v + 1)
                     torch.cuda.synchronize()
                     if best is None or st["kernel_ms"] < best["kernel_ms"]:
                         best = st
                 ev = best["evaluations"] / (best["kernel_ms"] * 1e-3)
-                rec = dict(dim=dim, df_mode=dfm, variant=v, n_cells=nc, n_species=len(sp["mass"]), kernel_ms=best["kernel_ms"],
-                           prepare_ms=best["prepare_ms"], reduce_ms=best["reduce_ms"], evals_per_s=ev, chunks=best["n_chunks"],
-                           frac_W85=ev * 85 / (peak * 1e12))
+                rec = dict(dim=dim, model=model, variant=v, n_cells=nc, n_species=len(sp["mass"]), kernel_ms=best["kernel_ms"],
+                           prepare_ms=best["prepare_ms"], evals_per_s=ev, chunks=best["n_chunks"], frac=ev * W[model] / (peak * 1e12),
+                           checksum=float(res.sum().item()))
                 out.append(rec)
                 print("SWEEP", json.dumps(rec), flush=True)
-                if best["kernel_ms"] > 300: clocks("v%d" % v)
-    mon.terminate()
     return out
 
 
@@ -111,6 +109,7 @@ if __name__ == "__main__":
         parity()
     if "sweep" in args:
         vs = list(range(8)) if "--variants" not in args else [int(v) for v in args[args.index("--variants") + 1].split(",")]
-        dims = (3, 2) if "--dim2" in args else (3,)
-        sweep(opt("--cells", 20000), opt("--species", 305), vs, dims)
+        dims = (3, 2) if "--dim2" in args else ((2,) if "--only2d" in args else (3,))
+        models = args[args.index("--models") + 1].split(",") if "--models" in args else ["lin14", "lince"]
+        sweep(opt("--cells", 20000), opt("--species", 305), vs, dims, models)
     print("done in %.1fs" % (time.time() - t0))
