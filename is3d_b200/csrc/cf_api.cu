@@ -212,7 +212,7 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
   // tile_variant: 0 = model default (tuned on B200, see profiles/), k > 0 = table entry k - 1 (tuning / tests)
   int variant;
   if (opt.tile_variant >= 1 && opt.tile_variant <= 16) variant = opt.tile_variant - 1;
-  else if (dim2_early) variant = 12;
+  else if (dim2_early) variant = (model == M_FEQMOD || model == M_VAH) ? 12 : 10;
   else variant = (model == M_FEQMOD || model == M_VAH) ? 12 : 11;
   int nyt, npt, ct;
   hot_variant_shape(variant, L.dim2, &nyt, &npt, &ct);

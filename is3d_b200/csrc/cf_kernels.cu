@@ -57,6 +57,20 @@ __device__ __forceinline__ void exp_neg_group(const double (&x)[N], double (&a)[
   }
 }
 
+// f_eq (1 + df) from a = e^{-x} (already evaluated) and the delta-f polynomial
+template <int MODEL>
+__device__ __forceinline__ double distribution_from_a(double a, double x, double s, double K2, double K3, double sign, int reg_thr)
+{
+  double dfs;
+  if (MODEL == M_LIN14) dfs = fma(K2 * x, x, s);
+  else dfs = fma(s, rcp_fast(x), K2 * x);
+  const double feq = occupation(a, sign);
+  const double feqbar = fma(-sign, feq, 1.0);
+  double df = (MODEL == M_JONAHLIN) ? fma(feqbar, dfs, K3) : feqbar * dfs;
+  df = clamp_unit(df, reg_thr);
+  return fma(feq, df, feq);
+}
+
 // Same as distribution() for a group of N evaluations, staged so that the N dependency chains can be interleaved and the
 // (rare) sub-normal branch is taken once per group.  pds[i] == 0 marks dead members.
 template <int MODEL, int N>
@@ -176,6 +190,7 @@ cf_kernel(const HotParams hp)
 
       // phi hoists: a few multiplies per (cell, phi), reused by every slot
       double q[NPT], pd[NPT], g0[NPT], g1[NPT], g2[NPT], g3[NPT];
+      double fq[NPT]; int fm[NPT];                    // SB == 3: e^{+q[k]} = fq 2^fm (factored exponential)
 #pragma unroll
       for (int k = 0; k < NPT; k++) {
         const double2 *pr = reinterpret_cast<const double2 *>(Ps + (c * NPT + k) * kRec);
@@ -192,6 +207,7 @@ cf_kernel(const HotParams hp)
           g1[k] = pT * v1.y;
           g2[k] = pT * v2.x;
           g3[k] = (MODEL == M_VAH) ? pT * v2.y : 0.0;                      // pT (Wx cos + Wy sin)
+          if (SB == 3) exp_neg_poly(-q[k], fq[k], fm[k]);
         }
       }
       auto slot = [&](int j, double *accj) {
@@ -291,6 +307,36 @@ cf_kernel(const HotParams hp)
                 s = fma(-g1[k], h1, s);
                 const double f = distribution<MODEL>(x, s, K2, K3, sign, reg_thr);
                 accumulate_outflow(accj[k], pds, f, thr);
+              }
+            }
+          } else if (SB == 3) {
+            // e^{-x} = e^{-mT Ax} e^{+pT Bx}: one exponential per slot and one per phi point instead of one per evaluation
+            double xs[NPT]; bool alive[NPT]; bool any = false;
+#pragma unroll
+            for (int k = 0; k < NPT; k++) { xs[k] = a - q[k]; alive[k] = exp_finite(xs[k]); any |= alive[k]; }
+            if (any) {
+              double pe; int ne;
+              exp_neg_poly(a, pe, ne);
+              double av[NPT]; bool rare = false;
+#pragma unroll
+              for (int k = 0; k < NPT; k++) {
+                const int n = ne + fm[k];
+                const double p = pe * fq[k];
+                av[k] = alive[k] ? exp_neg_fast(p, n) : 0.0;
+                rare |= alive[k] && exp_neg_is_rare(n);
+              }
+              if (__builtin_expect(rare, 0)) {
+#pragma unroll
+                for (int k = 0; k < NPT; k++) if (alive[k] && exp_neg_is_rare(ne + fm[k])) av[k] = exp_neg_rare(pe * fq[k], ne + fm[k]);
+              }
+#pragma unroll
+              for (int k = 0; k < NPT; k++) {
+                const double x = alive[k] ? xs[k] : 1.0;
+                const double pds = alive[k] ? fma(w, pd[k], cpm) : 0.0;
+                double s = h0 + g0[k];
+                s = fma(g2[k], h2, s);
+                s = fma(-g1[k], h1, s);
+                accumulate_outflow(accj[k], pds, distribution_from_a<MODEL>(av[k], x, s, K2, K3, sign, reg_thr), thr);
               }
             }
           } else {
@@ -403,10 +449,10 @@ cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, i
 struct Shape { int nyt, npt, ct, minb, sb; };
 static const Shape kShapes3D[] = {
   {7, 1, 16, 6, 0}, {7, 3, 16, 3, 0}, {7, 2, 16, 4, 0}, {7, 4, 16, 3, 0}, {7, 2, 16, 5, 0}, {3, 6, 16, 3, 0}, {7, 6, 16, 2, 0}, {7, 3, 16, 4, 0},
-  {7, 1, 16, 6, 2}, {7, 2, 16, 4, 1}, {7, 2, 16, 5, 1}, {7, 3, 16, 4, 1}, {7, 3, 16, 3, 1}, {7, 2, 16, 4, 2}, {7, 2, 16, 6, 1}, {7, 1, 16, 5, 2}};
+  {7, 3, 16, 4, 3}, {7, 2, 16, 4, 1}, {7, 3, 16, 3, 3}, {7, 3, 16, 4, 1}, {7, 3, 16, 3, 1}, {7, 4, 16, 3, 3}, {7, 2, 16, 6, 1}, {7, 6, 16, 2, 3}};
 static const Shape kShapes2D[] = {
   {1, 3, 1, 4, 0}, {1, 4, 1, 4, 0}, {1, 6, 1, 3, 0}, {1, 8, 1, 3, 0}, {1, 2, 1, 5, 0}, {1, 12, 1, 2, 0}, {1, 4, 1, 3, 0}, {1, 1, 1, 6, 0},
-  {1, 2, 1, 6, 1}, {1, 3, 1, 4, 1}, {1, 4, 1, 4, 1}, {1, 4, 1, 3, 1}, {1, 6, 1, 3, 1}, {1, 8, 1, 3, 1}, {1, 3, 1, 5, 1}, {1, 2, 1, 5, 1}};
+  {1, 6, 1, 3, 3}, {1, 3, 1, 4, 1}, {1, 4, 1, 4, 3}, {1, 4, 1, 3, 1}, {1, 6, 1, 3, 1}, {1, 8, 1, 3, 3}, {1, 3, 1, 5, 1}, {1, 12, 1, 2, 3}};
 constexpr int kNumVariants = 16;
 
 void hot_variant_shape(int variant, int dim2, int *nyt, int *npt, int *ct)
@@ -451,14 +497,14 @@ static cudaError_t launch_model(const HotParams &hp, int variant, cudaStream_t s
     }
     if constexpr (TUNE) {
       switch (variant) {
-        case 8: return launch_one<MODEL, 1, 2, true, 6, 1>(hp, st, smem_out);
+        case 8: return launch_one<MODEL, 1, 6, true, 3, 3>(hp, st, smem_out);
         case 9: return launch_one<MODEL, 1, 3, true, 4, 1>(hp, st, smem_out);
-        case 10: return launch_one<MODEL, 1, 4, true, 4, 1>(hp, st, smem_out);
+        case 10: return launch_one<MODEL, 1, 4, true, 4, 3>(hp, st, smem_out);
         case 11: return launch_one<MODEL, 1, 4, true, 3, 1>(hp, st, smem_out);
         case 12: return launch_one<MODEL, 1, 6, true, 3, 1>(hp, st, smem_out);
-        case 13: return launch_one<MODEL, 1, 8, true, 3, 1>(hp, st, smem_out);
+        case 13: return launch_one<MODEL, 1, 8, true, 3, 3>(hp, st, smem_out);
         case 14: return launch_one<MODEL, 1, 3, true, 5, 1>(hp, st, smem_out);
-        case 15: return launch_one<MODEL, 1, 2, true, 5, 1>(hp, st, smem_out);
+        case 15: return launch_one<MODEL, 1, 12, true, 2, 3>(hp, st, smem_out);
         default: break;
       }
     }
@@ -476,14 +522,14 @@ static cudaError_t launch_model(const HotParams &hp, int variant, cudaStream_t s
   }
   if constexpr (TUNE) {
     switch (variant) {
-      case 8: return launch_one<MODEL, 7, 1, false, 6, 2>(hp, st, smem_out);
+      case 8: return launch_one<MODEL, 7, 3, false, 4, 3>(hp, st, smem_out);
       case 9: return launch_one<MODEL, 7, 2, false, 4, 1>(hp, st, smem_out);
-      case 10: return launch_one<MODEL, 7, 2, false, 5, 1>(hp, st, smem_out);
+      case 10: return launch_one<MODEL, 7, 3, false, 3, 3>(hp, st, smem_out);
       case 11: return launch_one<MODEL, 7, 3, false, 4, 1>(hp, st, smem_out);
       case 12: return launch_one<MODEL, 7, 3, false, 3, 1>(hp, st, smem_out);
-      case 13: return launch_one<MODEL, 7, 2, false, 4, 2>(hp, st, smem_out);
+      case 13: return launch_one<MODEL, 7, 4, false, 3, 3>(hp, st, smem_out);
       case 14: return launch_one<MODEL, 7, 2, false, 6, 1>(hp, st, smem_out);
-      case 15: return launch_one<MODEL, 7, 1, false, 5, 2>(hp, st, smem_out);
+      case 15: return launch_one<MODEL, 7, 6, false, 2, 3>(hp, st, smem_out);
       default: break;
     }
   }
