@@ -123,6 +123,11 @@ int is3d_b200_measure_fp64_sustained(double seconds, double *tflops);
  * results/dN_dy_*.dat with the reference's formats.  If dN_raw != NULL it receives the spectra (n_raw doubles max). */
 int is3d_b200_run_workdir(const char *workdir, double *dN_raw, int64_t n_raw, int32_t *mcid_out, int32_t n_mcid_max,
                           is3d_stats *stats);
+/* Same with the freeze-out cells passed in memory (reference: IS3D::read_fo_surf_from_memory + run_particlization(0),
+ * src/cpp/iS3D.cpp:26-71): parameters, particle list and tables still come from `workdir`. */
+int is3d_b200_run_surface(const char *workdir, const is3d_surface *surface, double *dN_raw, int64_t n_raw,
+                          int32_t *mcid_out, int32_t n_mcid_max, is3d_stats *stats);
+
 /* Host-side table builders for callers that drive is3d_b200_smooth_spectra() directly (no working directory):
  *  - surface averages T, E, P, muB, nB weighted as in FO_data_reader::read_surf_VH (readindata.cpp:423-466), passed through
  *    the reference's 15-significant-digit side file round trip (average_thermodynamic_quantities.dat);

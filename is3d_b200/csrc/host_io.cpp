@@ -207,15 +207,16 @@ bool read_surface(const std::string &workdir, const SurfaceFlags &fl, SurfaceDat
   for (char c : text) if (c == '\n') n++;
   s->n = n;
   const int mode = fl.mode;
-  if (mode != 0 && mode != 1 && mode != 2) {
-    if (err) *err = "surface mode " + std::to_string(mode) + " is not part of the smooth-spectra path yet (modes 0, 1, 2 are)";
+  if (mode < 0 || mode > 7 || mode == 3) {
+    if (err) *err = "surface mode " + std::to_string(mode) + " has no smooth-spectra kernel (the reference reads mode 3 but never dispatches it)";
     return false;
   }
   auto rs = [&](std::vector<double> &v) { v.assign((size_t)n, 0.0); };
   rs(s->tau); rs(s->x); rs(s->y); rs(s->eta); rs(s->dat); rs(s->dax); rs(s->day); rs(s->dan); rs(s->ux); rs(s->uy); rs(s->un);
   rs(s->E); rs(s->T); rs(s->P); rs(s->pixx); rs(s->pixy); rs(s->pixn); rs(s->piyy); rs(s->piyn); rs(s->bulkPi);
   rs(s->muB); rs(s->nB); rs(s->Vx); rs(s->Vy); rs(s->Vn);
-  if (mode != 1) { rs(s->pitt); rs(s->pitx); rs(s->pity); rs(s->pitn); rs(s->pinn); }
+  const bool full_pi = (mode == 0 || mode == 2 || mode == 4 || mode == 6);     // formats that store all ten pi components
+  if (full_pi) { rs(s->pitt); rs(s->pitx); rs(s->pity); rs(s->pitn); rs(s->pinn); }
   if (mode == 2) { rs(s->PL); rs(s->Wx); rs(s->Wy); rs(s->Lambda); rs(s->aL); rs(s->c0); rs(s->c1); rs(s->c2); rs(s->c3); rs(s->c4); }
 
   Tokens tk{text.data(), text.data() + text.size()};
@@ -223,35 +224,72 @@ bool read_surface(const std::string &workdir, const SurfaceFlags &fl, SurfaceDat
   bool short_file = false;
   auto rd = [&](double *v) { if (!tk.next(v)) { short_file = true; *v = 0.0; } };
   auto rd_gev = [&](double *v) { double t; rd(&t); *v = t * kHbarC; };      // fm^-n -> GeV fm^(1-n), one multiply
+  const bool writes_averages = (mode != 2 && mode != 5);                    // readindata.cpp: modes 2, 3, 5 never write the side file
   for (int64_t i = 0; i < n; i++) {
-    double skip;
+    double skip, muB = 0.0, nB = 0.0;
     rd(&s->tau[i]); rd(&s->x[i]); rd(&s->y[i]); rd(&s->eta[i]);
-    rd(&s->dat[i]); rd(&s->dax[i]); rd(&s->day[i]); rd(&s->dan[i]);
-    if (fl.dimension == 2 && s->dan[i] != 0 && mode == 0) {
-      if (err) *err = "2+1d boost invariant surface read-in error at cell # " + std::to_string(i) + ": dsigma_eta is not zero";
-      return false;                                                           // mode 0 exits here (readindata.cpp:183-187)
-    }
-    if (mode != 1) rd(&skip);                                                 // u^tau column (recomputed from u^i)
-    rd(&s->ux[i]); rd(&s->uy[i]); rd(&s->un[i]);
-    double Efile, Tfile, Pfile, PLfile = 0;                                    // file units (fm^-4, fm^-1, fm^-4)
-    rd(&Efile); rd(&Tfile); rd(&Pfile);
-    s->E[i] = Efile * kHbarC; s->T[i] = Tfile * kHbarC; s->P[i] = Pfile * kHbarC;
-    if (mode == 2) { rd(&PLfile); s->PL[i] = PLfile * kHbarC; }
-    if (mode != 1) { rd_gev(&s->pitt[i]); rd_gev(&s->pitx[i]); rd_gev(&s->pity[i]); rd_gev(&s->pitn[i]); }
-    rd_gev(&s->pixx[i]); rd_gev(&s->pixy[i]); rd_gev(&s->pixn[i]); rd_gev(&s->piyy[i]); rd_gev(&s->piyn[i]);
-    if (mode != 1) rd_gev(&s->pinn[i]);
-    if (mode == 2) { double wt, wn; rd(&wt); rd_gev(&s->Wx[i]); rd_gev(&s->Wy[i]); rd(&wn); }
-    rd_gev(&s->bulkPi[i]);
-    double muB = 0.0, nB = 0.0;
-    if (mode != 2) {
-      if (fl.include_baryon) { rd_gev(&muB); s->muB[i] = muB; }
-      if (fl.include_baryondiff_deltaf) {
-        rd(&nB); s->nB[i] = nB;
-        if (mode == 0) rd(&skip);                                             // V^tau column of the old format
-        rd(&s->Vx[i]); rd(&s->Vy[i]); rd(&s->Vn[i]);
+    const double tau = s->tau[i];
+    if (mode == 4 || mode == 6 || mode == 7) {
+      // boost-invariant formats (MUSIC old :552-681, MUSIC new :683-810, hic-eventgen :1059-1196): eta := 0, dsigma stored / tau
+      s->eta[i] = 0.0;
+      double a;
+      rd(&a); s->dat[i] = a * tau; rd(&a); s->dax[i] = a * tau; rd(&a); s->day[i] = a * tau; rd(&a); s->dan[i] = a * tau;
+      if (mode != 4 || fl.dimension == 2) s->dan[i] = 0.0;
+    } else {
+      rd(&s->dat[i]); rd(&s->dax[i]); rd(&s->day[i]); rd(&s->dan[i]);
+      if (fl.dimension == 2 && s->dan[i] != 0 && mode == 0) {
+        if (err) *err = "2+1d boost invariant surface read-in error at cell # " + std::to_string(i) + ": dsigma_eta is not zero";
+        return false;                                                         // mode 0 exits here (readindata.cpp:183-187)
       }
-      // surface averages weighted with |u.dsigma| + sqrt(|(u.dsigma)^2 - dsigma.dsigma|) (readindata.cpp:423-452)
-      const double tau = s->tau[i], ux = s->ux[i], uy = s->uy[i], un = s->un[i];
+    }
+    double PLfile = 0, Pfile = 0, Tfile = 0;
+    if (mode == 7) {
+      // velocities instead of u^mu; every dissipative quantity already in GeV units
+      double vx, vy, vn; rd(&vx); rd(&vy); rd(&vn);
+      const double ut = std::sqrt(1.0 / (1.0 - (vx * vx) - (vy * vy)));
+      s->ux[i] = ut * vx; s->uy[i] = ut * vy; s->un[i] = 0.0;
+      double a;
+      rd(&skip); rd(&skip); rd(&skip); rd(&skip);                             // pi^tt, pi^tx, pi^ty, pi^tz
+      rd(&s->pixx[i]); rd(&s->pixy[i]); rd(&a); s->pixn[i] = a / tau; rd(&s->piyy[i]); rd(&a); s->piyn[i] = a / tau; rd(&skip);
+      rd(&s->bulkPi[i]); rd(&s->T[i]); rd(&s->E[i]); rd(&s->P[i]); rd(&muB); s->muB[i] = muB;
+    } else {
+      if (mode == 0 || mode == 2 || mode == 4 || mode == 6) rd(&skip);          // u^tau column (recomputed from u^i)
+      rd(&s->ux[i]); rd(&s->uy[i]); rd(&s->un[i]);
+      if (mode == 4 || mode == 6) s->un[i] = s->un[i] / tau;
+      double Efile;
+      rd(&Efile); rd(&Tfile);
+      s->E[i] = Efile * kHbarC; s->T[i] = Tfile * kHbarC;
+      if (mode == 4 || mode == 6) {
+        rd_gev(&muB); s->muB[i] = muB;                                           // always present in the MUSIC formats
+        if (mode == 6) { rd(&skip); rd(&skip); }                                 // mu_S, mu_C
+        double sdens; rd(&sdens);
+        s->P[i] = sdens * s->T[i] - s->E[i];                                     // p = T s - e
+      } else {
+        rd(&Pfile); s->P[i] = Pfile * kHbarC;
+      }
+      if (mode == 2) { rd(&PLfile); s->PL[i] = PLfile * kHbarC; }
+      if (full_pi) { rd_gev(&s->pitt[i]); rd_gev(&s->pitx[i]); rd_gev(&s->pity[i]); rd_gev(&s->pitn[i]); }
+      rd_gev(&s->pixx[i]); rd_gev(&s->pixy[i]); rd_gev(&s->pixn[i]); rd_gev(&s->piyy[i]); rd_gev(&s->piyn[i]);
+      if (full_pi) rd_gev(&s->pinn[i]);
+      if (mode == 4 || mode == 6) {                                              // MUSIC stores tau * pi^{mu eta}
+        s->pitn[i] = s->pitn[i] / tau; s->pixn[i] = s->pixn[i] / tau; s->piyn[i] = s->piyn[i] / tau; s->pinn[i] = s->pinn[i] / tau / tau;
+      }
+      if (mode == 2) { double wt, wn; rd(&wt); rd_gev(&s->Wx[i]); rd_gev(&s->Wy[i]); rd(&wn); }
+      rd_gev(&s->bulkPi[i]);
+      if (mode == 0 || mode == 1 || mode == 5) {
+        if (fl.include_baryon) { rd_gev(&muB); s->muB[i] = muB; }
+        if (fl.include_baryondiff_deltaf) {
+          rd(&nB); s->nB[i] = nB;
+          if (mode == 0 || mode == 5) rd(&skip);                                  // V^tau column
+          rd(&s->Vx[i]); rd(&s->Vy[i]); rd(&s->Vn[i]);
+        }
+        if (mode == 5) for (int k = 0; k < 6; k++) rd(&skip);                    // thermal vorticity, unused by this path
+      }
+    }
+    if (writes_averages) {
+      // surface averages weighted with |u.dsigma| + sqrt(|(u.dsigma)^2 - dsigma.dsigma|) (readindata.cpp:423-452).
+      // (mode 7: the reference evaluates u.dsigma from uninitialised locals -- undefined behaviour; the stored u^mu is used here)
+      const double ux = s->ux[i], uy = s->uy[i], un = s->un[i];
       const double ut = std::sqrt(1.0 + ux * ux + uy * uy + tau * tau * un * un);
       const double dat = s->dat[i], dax = s->dax[i], day = s->day[i], dan = s->dan[i];
       const double udsigma = ut * dat + ux * dax + uy * day + un * dan;
@@ -259,7 +297,8 @@ bool read_surface(const std::string &workdir, const SurfaceFlags &fl, SurfaceDat
       const double mag = std::fabs(udsigma) + std::sqrt(std::fabs(udsigma * udsigma - dsds));
       volume += mag;
       Eavg += (s->E[i] * mag); Tavg += (s->T[i] * mag); Pavg += (s->P[i] * mag); muBavg += (muB * mag); nBavg += (nB * mag);
-    } else {
+    }
+    if (mode == 2) {
       // conformal factorisation: alpha_L from PL/P, Lambda from T (readindata.cpp:905-918)
       if (!((PLfile / Pfile) < 3.0)) { if (err) *err = "pl is too large, stopping anisotropic variables"; return false; }
       const double aLv = aL_fit(PLfile / Pfile);
@@ -269,22 +308,22 @@ bool read_surface(const std::string &workdir, const SurfaceFlags &fl, SurfaceDat
   }
   if (short_file) { if (err) *err = "surface file " + path + " has fewer values than " + std::to_string(n) + " cells need"; return false; }
 
-  if (mode != 2) {
+  const std::string apath = workdir + "/average_thermodynamic_quantities.dat";
+  if (writes_averages) {
     Tavg /= volume; Eavg /= volume; Pavg /= volume; muBavg /= volume; nBavg /= volume;
     // side file: 15 significant digits, default float format (readindata.cpp:463-466), re-read by
     // Plasma::load_thermodynamic_averages (:90-100) -- the round trip is part of the reference's arithmetic
-    const std::string apath = workdir + "/average_thermodynamic_quantities.dat";
     FILE *f = std::fopen(apath.c_str(), "w");
     if (!f) { if (err) *err = "cannot write " + apath; return false; }
     std::fprintf(f, "%.15g\n%.15g\n%.15g\n%.15g\n%.15g", Tavg, Eavg, Pavg, muBavg, nBavg);
     std::fclose(f);
-    f = std::fopen(apath.c_str(), "r");
-    if (!f || std::fscanf(f, "%lf\n%lf\n%lf\n%lf\n%lf", &s->avg[0], &s->avg[1], &s->avg[2], &s->avg[3], &s->avg[4]) != 5) {
-      if (f) std::fclose(f);
-      if (err) *err = "cannot re-read " + apath; return false;
-    }
-    std::fclose(f);
-    s->averages_written = true;
+  }
+  if (mode != 2) {
+    // modes that do not write the file read whatever an earlier run left there, like the reference
+    FILE *f = std::fopen(apath.c_str(), "r");
+    if (f && std::fscanf(f, "%lf\n%lf\n%lf\n%lf\n%lf", &s->avg[0], &s->avg[1], &s->avg[2], &s->avg[3], &s->avg[4]) == 5) s->averages_written = true;
+    if (f) std::fclose(f);
+    if (!s->averages_written && (writes_averages || fl.df_mode == 4)) { if (err) *err = "cannot read " + apath; return false; }
   }
   return true;
 }

@@ -201,6 +201,38 @@ static int load_problem(const std::string &wd, bool need_surface, Problem *p, st
   return IS3D_OK;
 }
 
+static int run_problem(const std::string &wd, Problem &P, const is3d_surface &s, double *dN_raw, int64_t n_raw, int32_t *mcid_out,
+                       int32_t n_mcid_max, is3d_stats *stats, std::string *err_out)
+{
+  std::string &err = *err_out;
+  const Grids &g = P.g; const DfTables &dft = P.dft; const Laguerre &gla = P.gla;
+  const int npart = (int)P.mcid.size();
+  is3d_species sp{npart, P.mass.data(), P.sign.data(), P.degen.data(), P.baryon.data()};
+  is3d_grid gr{(int32_t)g.pT.rows, (int32_t)g.phi.rows, (int32_t)g.y.rows, (int32_t)g.eta.rows,
+               g.pT.cols[0].data(), g.phi.cols[0].data(), g.y.cols[0].data(), g.eta.cols[0].data(), g.eta.cols[1].data()};
+  is3d_df_tables dt; std::memset(&dt, 0, sizeof(dt));
+  dt.n_T = dft.n_T; dt.T = dft.T.data(); dt.c0 = dft.c0.data(); dt.c1 = dft.c1.data(); dt.c2 = dft.c2.data(); dt.c3 = dft.c3.data();
+  dt.c4 = dft.c4.data(); dt.F = dft.F.data(); dt.G = dft.G.data(); dt.betabulk = dft.betabulk.data(); dt.betaV = dft.betaV.data();
+  dt.betapi = dft.betapi.data();
+  if (!dft.jonah_x.empty()) {
+    dt.n_jonah = (int32_t)dft.jonah_x.size(); dt.jonah_x = dft.jonah_x.data(); dt.jonah_lambda2 = dft.jonah_lambda2.data();
+    dt.jonah_z = dft.jonah_z.data(); dt.bulkPi_over_Peq_max = dft.bulkPi_over_Peq_max;
+  }
+  is3d_laguerre la{gla.points, gla.root[1].data(), gla.weight[1].data(), gla.root[2].data(), gla.weight[2].data()};
+  const size_t n_bins = (size_t)npart * g.pT.rows * g.phi.rows * g.y.rows;
+  std::vector<double> dN(n_bins, 0.0);
+  is3d_stats st; std::memset(&st, 0, sizeof(st));
+  const int rc = is3d_b200_smooth_spectra(&P.fl, &s, &sp, &gr, &dt, &la, nullptr, dN.data(), &st);
+  if (stats) *stats = st;
+  if (rc != IS3D_OK) { err = std::string("spectra kernel failed: ") + is3d_b200_last_error(); return rc; }
+  if (P.fl.mode != 2 && (P.fl.df_mode == 3 || P.fl.df_mode == 4))
+    std::cout << std::setw(5) << std::setprecision(4) << "\nfeqmod breaks down for " << st.cells_feqmod_breakdown << " cells\n" << std::endl;
+  if (dN_raw) std::memcpy(dN_raw, dN.data(), sizeof(double) * (size_t)std::min<int64_t>(n_raw, (int64_t)n_bins));
+  if (mcid_out) for (int i = 0; i < npart && i < n_mcid_max; i++) mcid_out[i] = P.mcid[i];
+  if (!write_spectra_files(wd, dN, P.mcid, g, P.fl.dimension, &err)) return IS3D_ERR_IO;
+  return IS3D_OK;
+}
+
 }  // namespace is3d
 
 using namespace is3d;
@@ -214,47 +246,44 @@ extern "C" int is3d_b200_run_workdir(const char *workdir, double *dN_raw, int64_
   Problem P;
   int rc = load_problem(wd, true, &P, &err);
   if (rc != IS3D_OK) return fail(rc);
-  const SurfaceData &sf = P.sf; const Grids &g = P.g; const DfTables &dft = P.dft; const Laguerre &gla = P.gla;
-  const int npart = (int)P.mcid.size(), mode = P.fl.mode;
-
-  // ---- spectra on the GPU
+  const SurfaceData &sf = P.sf;
   is3d_surface s; std::memset(&s, 0, sizeof(s));
   s.n_cells = sf.n;
   s.tau = sf.tau.data(); s.eta = sf.eta.data(); s.dat = sf.dat.data(); s.dax = sf.dax.data(); s.day = sf.day.data(); s.dan = sf.dan.data();
   s.ux = sf.ux.data(); s.uy = sf.uy.data(); s.un = sf.un.data(); s.T = sf.T.data(); s.P = sf.P.data(); s.E = sf.E.data();
   s.pixx = sf.pixx.data(); s.pixy = sf.pixy.data(); s.pixn = sf.pixn.data(); s.piyy = sf.piyy.data(); s.piyn = sf.piyn.data();
   s.bulkPi = sf.bulkPi.data(); s.muB = sf.muB.data(); s.nB = sf.nB.data(); s.Vx = sf.Vx.data(); s.Vy = sf.Vy.data(); s.Vn = sf.Vn.data();
-  if (mode == 2) {
+  if (P.fl.mode == 2) {
     s.pitt = sf.pitt.data(); s.pitx = sf.pitx.data(); s.pity = sf.pity.data(); s.pitn = sf.pitn.data(); s.pinn = sf.pinn.data();
     s.Wx = sf.Wx.data(); s.Wy = sf.Wy.data(); s.Lambda = sf.Lambda.data(); s.aL = sf.aL.data();
     s.c0 = sf.c0.data(); s.c1 = sf.c1.data(); s.c2 = sf.c2.data(); s.c3 = sf.c3.data(); s.c4 = sf.c4.data();
   }
-  is3d_species sp{npart, P.mass.data(), P.sign.data(), P.degen.data(), P.baryon.data()};
-  is3d_grid gr{(int32_t)g.pT.rows, (int32_t)g.phi.rows, (int32_t)g.y.rows, (int32_t)g.eta.rows,
-               g.pT.cols[0].data(), g.phi.cols[0].data(), g.y.cols[0].data(), g.eta.cols[0].data(), g.eta.cols[1].data()};
-  is3d_df_tables dt; std::memset(&dt, 0, sizeof(dt));
-  dt.n_T = dft.n_T; dt.T = dft.T.data(); dt.c0 = dft.c0.data(); dt.c1 = dft.c1.data(); dt.c2 = dft.c2.data(); dt.c3 = dft.c3.data();
-  dt.c4 = dft.c4.data(); dt.F = dft.F.data(); dt.G = dft.G.data(); dt.betabulk = dft.betabulk.data(); dt.betaV = dft.betaV.data();
-  dt.betapi = dft.betapi.data();
-  if (!dft.jonah_x.empty()) {
-    dt.n_jonah = (int32_t)dft.jonah_x.size(); dt.jonah_x = dft.jonah_x.data(); dt.jonah_lambda2 = dft.jonah_lambda2.data();
-    dt.jonah_z = dft.jonah_z.data(); dt.bulkPi_over_Peq_max = dft.bulkPi_over_Peq_max;
+  rc = run_problem(wd, P, s, dN_raw, n_raw, mcid_out, n_mcid_max, stats, &err);
+  return rc == IS3D_OK ? rc : fail(rc);
+}
+
+// In-memory surface (the reference's IS3D::read_fo_surf_from_memory + run_particlization(0), iS3D.cpp:26-71, 99-134):
+// the freeze-out cells come from the caller, everything else (parameters, particle list, tables) from `workdir`.
+// Unlike the reference -- which leaves the averages side file stale on this path -- the df_mode 4 tables are built from
+// the surface that was actually passed in.
+extern "C" int is3d_b200_run_surface(const char *workdir, const is3d_surface *surface, double *dN_raw, int64_t n_raw,
+                                     int32_t *mcid_out, int32_t n_mcid_max, is3d_stats *stats)
+{
+  const std::string wd = (workdir && *workdir) ? workdir : ".";
+  std::string err;
+  auto fail = [&](int code) { g_host_error = err; std::fprintf(stderr, "is3d_b200: %s\n", err.c_str()); return code; };
+  if (!surface) { err = "NULL surface"; return fail(IS3D_ERR_ARGUMENT); }
+  Problem P;
+  int rc = load_problem(wd, false, &P, &err);
+  if (rc != IS3D_OK) return fail(rc);
+  if (P.fl.mode != 2 && P.fl.df_mode == 4) {
+    double avg[5];
+    rc = is3d_b200_surface_averages(surface, avg);
+    if (rc != IS3D_OK) { err = "cannot average an empty surface"; return fail(rc); }
+    compute_jonah_tables(P.pdg, avg[0], P.gla, &P.dft);
   }
-  is3d_laguerre la{gla.points, gla.root[1].data(), gla.weight[1].data(), gla.root[2].data(), gla.weight[2].data()};
-
-  const size_t n_bins = (size_t)npart * g.pT.rows * g.phi.rows * g.y.rows;
-  std::vector<double> dN(n_bins, 0.0);
-  is3d_stats st; std::memset(&st, 0, sizeof(st));
-  rc = is3d_b200_smooth_spectra(&P.fl, &s, &sp, &gr, &dt, &la, nullptr, dN.data(), &st);
-  if (stats) *stats = st;
-  if (rc != IS3D_OK) { err = std::string("spectra kernel failed: ") + is3d_b200_last_error(); return fail(rc); }
-  if (P.fl.df_mode == 3 || P.fl.df_mode == 4)
-    std::cout << std::setw(5) << std::setprecision(4) << "\nfeqmod breaks down for " << st.cells_feqmod_breakdown << " cells\n" << std::endl;
-
-  if (dN_raw) std::memcpy(dN_raw, dN.data(), sizeof(double) * (size_t)std::min<int64_t>(n_raw, (int64_t)n_bins));
-  if (mcid_out) for (int i = 0; i < npart && i < n_mcid_max; i++) mcid_out[i] = P.mcid[i];
-  if (!write_spectra_files(wd, dN, P.mcid, g, P.fl.dimension, &err)) return fail(IS3D_ERR_IO);
-  return IS3D_OK;
+  rc = run_problem(wd, P, *surface, dN_raw, n_raw, mcid_out, n_mcid_max, stats, &err);
+  return rc == IS3D_OK ? rc : fail(rc);
 }
 
 // Writers only: takes a spectra array (reference layout) and produces the results/ files for `workdir`.

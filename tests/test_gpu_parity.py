@@ -258,3 +258,24 @@ def test_two_gpu_nccl(fx, tmp_path):
     d0 = np.load(tmp_path / "dN_0.npy"); ref = np.load(tmp_path / "dN_single.npy")
     nz = ref != 0
     assert np.max(np.abs(d0[nz] - ref[nz]) / ref[nz]) < 1e-12 and np.all(d0[~nz] == 0)
+
+
+def test_in_memory_surface_entry(fx):
+    """is3d_b200_run_surface (the read_fo_surf_from_memory seam): same spectra as the file path, df_mode 4 tables included"""
+    gold = load_golden("s3_df4")
+    lib = api.lib()
+    fl, cells, sp, g, tab, gla = problem_from_recipe(gold["recipe"], fx)
+    with tempfile.TemporaryDirectory() as wd:
+        workdir.materialize(wd, surface_columns=surface_columns(gold["recipe"], fx), chosen=gold["recipe"]["chosen"], fixture=fx,
+                            operation=1, mode=1, **gold["recipe"]["params"])
+        os.remove(os.path.join(wd, "input", "surface.dat"))                       # the cells come from memory
+        m = api._Marshal(False)
+        sf = api.Surface(); sf.n_cells = len(cells["tau"])
+        for k in api.SURFACE_FIELDS:
+            if k in cells:
+                setattr(sf, k, m.cells(cells[k]))
+        dN = np.zeros(gold["dN"].size); st = api.Stats()
+        rc = lib.is3d_b200_run_surface(wd.encode(), C.byref(sf), dN.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(dN.size), None, 0, C.byref(st))
+        assert rc == 0
+        assert compare(dN, gold["dN"])["ok"]
+        assert os.path.getsize(os.path.join(wd, "results", "dN_pTdpTdphidy.dat")) > 0

@@ -200,3 +200,51 @@ def test_surface_reader_mode2_and_vah_coefficients(fx):
         assert np.array_equal(d[k], ref[k]), k
     for k in ("aL", "Lambda", "c0", "c1", "c2", "c3", "c4"):
         assert np.allclose(d[k], ref[k], rtol=1e-12, atol=0), k
+
+
+def _alt_format_columns(mode, base):
+    """Re-express a mode-1 (20 column) surface in the column layout of another reader (values chosen so that both describe
+    the same physical cells where the formats allow it)."""
+    hb = synthetic.HBARC
+    tau = base[:, 0]
+    z = np.zeros(len(base))
+    ut = np.sqrt(1 + base[:, 8] ** 2 + base[:, 9] ** 2 + (tau * base[:, 10]) ** 2)
+    E, T, P = base[:, 11], base[:, 12], base[:, 13]
+    pixx, pixy, pixn, piyy, piyn, bulk = (base[:, k] for k in range(14, 20))
+    if mode in (4, 6):
+        s = (E + P) / T                                   # entropy density such that p = T s - e
+        head = [tau, base[:, 1], base[:, 2], base[:, 3], base[:, 4] / tau, base[:, 5] / tau, base[:, 6] / tau, base[:, 7] / tau,
+                ut, base[:, 8], base[:, 9], base[:, 10] * tau, E, T, z + 0.01]
+        if mode == 6:
+            head += [z, z]
+        head += [s, z, z, z, z, pixx, pixy, pixn * tau, piyy, piyn * tau, z, bulk]
+        return np.column_stack(head)
+    if mode == 7:
+        vx, vy = base[:, 8] / ut, base[:, 9] / ut
+        return np.column_stack([tau, base[:, 1], base[:, 2], base[:, 3], base[:, 4] / tau, base[:, 5] / tau, base[:, 6] / tau, z,
+                                vx, vy, z, z, z, z, z, pixx * hb, pixy * hb, pixn * hb * tau, piyy * hb, piyn * hb * tau, z,
+                                bulk * hb, T * hb, E * hb, P * hb, z])
+    if mode == 5:
+        return np.column_stack([base, z + 0.1, z + 0.2, z + 0.3, z + 0.4, z + 0.5, z + 0.6])
+    raise ValueError(mode)
+
+
+@pytest.mark.skipif(cfo.ref_binary() is None, reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("mode,dimension", [(4, 2), (6, 2), (7, 2), (5, 3), (4, 3)])
+def test_other_surface_formats_against_reference(fx, mode, dimension):
+    """MUSIC (old/new), hic-eventgen and vorticity surface formats: cells parsed by the C++ reader + oracle kernel must give
+    the spectra the reference computes from the same file (bit for bit)."""
+    base = synthetic.surface_vh(12, 100 + mode, three_d=(dimension == 3))
+    cols = _alt_format_columns(mode, base)
+    with tempfile.TemporaryDirectory() as wd:
+        workdir.materialize(wd, surface_columns=cols, chosen="chosen_pikp", fixture=fx, operation=1, mode=mode, hrg_eos=1,
+                            dimension=dimension, df_mode=1)
+        if mode == 5:      # this reader never writes the averages side file; the reference would read a stale one
+            open(os.path.join(wd, "average_thermodynamic_quantities.dat"), "w").write("0.15\n0.3\n0.05\n0\n0")
+        ref, info = cfo.run_reference(wd)
+        d = host_dump(wd)
+    cells = {k: d[k] for k in ("tau", "eta", "dat", "dax", "day", "dan", "ux", "uy", "un", "E", "T", "P", "pixx", "pixy", "pixn", "piyy", "piyn", "bulkPi")}
+    sp = tables.species(fx, 1, "chosen_pikp"); g = tables.grid(fx); tab = tables.df_tables(fx, 1)
+    dN, skipped, _ = cfo.smooth(tables.flags(df_mode=1, dimension=dimension), cells, sp, g, tab, None)
+    assert len(cells["tau"]) == 12 and skipped == 0
+    assert np.array_equal(dN, ref)
