@@ -42,18 +42,20 @@ __device__ __forceinline__ double distribution(double x, double s, double K2, do
 // evaluated as soon as one of its members is alive.
 // e^{-x[i]} for a group of N arguments, staged so that the N polynomial chains interleave and the (rare) sub-normal branch
 // is taken once per group
+// Dead members (alive[i] false: x beyond the overflow threshold) are NOT sanitised: their results are garbage and must be
+// discarded by the caller (the accumulate is predicated off through a -0.0 weight), which keeps selects off the chain.
 template <int N>
-__device__ __forceinline__ void exp_neg_group(const double (&x)[N], double (&a)[N])
+__device__ __forceinline__ void exp_neg_group(const double (&x)[N], const bool (&alive)[N], double (&a)[N])
 {
   double p[N]; int n[N];
   bool rare = false;
 #pragma unroll
-  for (int i = 0; i < N; i++) { exp_neg_poly(x[i], p[i], n[i]); rare |= exp_neg_is_rare(n[i]); }
+  for (int i = 0; i < N; i++) { exp_neg_poly(x[i], p[i], n[i]); rare |= alive[i] && exp_neg_is_rare(n[i]); }
 #pragma unroll
   for (int i = 0; i < N; i++) a[i] = exp_neg_fast(p[i], n[i]);
   if (__builtin_expect(rare, 0)) {
 #pragma unroll
-    for (int i = 0; i < N; i++) if (exp_neg_is_rare(n[i])) a[i] = exp_neg_rare(p[i], n[i]);
+    for (int i = 0; i < N; i++) if (alive[i] && exp_neg_is_rare(n[i])) a[i] = exp_neg_rare(p[i], n[i]);
   }
 }
 
@@ -74,15 +76,15 @@ __device__ __forceinline__ double distribution_from_a(double a, double x, double
 // Same as distribution() for a group of N evaluations, staged so that the N dependency chains can be interleaved and the
 // (rare) sub-normal branch is taken once per group.  pds[i] == 0 marks dead members.
 template <int MODEL, int N>
-__device__ __forceinline__ void distribution_group(const double (&x)[N], const double (&s)[N], double K2, double K3, double sign,
-                                                   int reg_thr, double (&f)[N])
+__device__ __forceinline__ void distribution_group(const double (&x)[N], const bool (&alive)[N], const double (&s)[N], double K2, double K3,
+                                                   double sign, int reg_thr, double (&f)[N])
 {
   double p[N], a[N], dfs[N]; int n[N];
   bool rare = false;
 #pragma unroll
   for (int i = 0; i < N; i++) {
     exp_neg_poly(x[i], p[i], n[i]);
-    rare |= exp_neg_is_rare(n[i]);
+    rare |= alive[i] && exp_neg_is_rare(n[i]);
     if (MODEL == M_LIN14) dfs[i] = fma(K2 * x[i], x[i], s[i]);
     else dfs[i] = fma(s[i], rcp_fast(x[i]), K2 * x[i]);
   }
@@ -90,7 +92,7 @@ __device__ __forceinline__ void distribution_group(const double (&x)[N], const d
   for (int i = 0; i < N; i++) a[i] = exp_neg_fast(p[i], n[i]);
   if (__builtin_expect(rare, 0)) {
 #pragma unroll
-    for (int i = 0; i < N; i++) if (exp_neg_is_rare(n[i])) a[i] = exp_neg_rare(p[i], n[i]);
+    for (int i = 0; i < N; i++) if (alive[i] && exp_neg_is_rare(n[i])) a[i] = exp_neg_rare(p[i], n[i]);
   }
 #pragma unroll
   for (int i = 0; i < N; i++) {
@@ -228,19 +230,18 @@ cf_kernel(const HotParams hp)
               }
             }
           } else {
-            double xv[NPT], pv[NPT], av[NPT]; bool any = false;
+            double xv[NPT], pv[NPT], av[NPT]; bool lv[NPT]; bool any = false;
 #pragma unroll
             for (int k = 0; k < NPT; k++) {
               double E2 = h0 + g0[k];
               E2 = fma(e1, g1[k], E2); E2 = fma(e2, g2[k], E2); E2 = fma(e3, g3[k], E2);
-              const double x = sqrt_fast(E2);
-              const bool alive = exp_finite(x);
-              any |= alive;
-              xv[k] = alive ? x : 1.0;
-              pv[k] = alive ? fma(w, pd[k], cpm) : 0.0;
+              xv[k] = sqrt_fast(E2);
+              lv[k] = exp_finite(xv[k]);
+              any |= lv[k];
+              pv[k] = lv[k] ? fma(w, pd[k], cpm) : -0.0;
             }
             if (any) {
-              exp_neg_group<NPT>(xv, av);
+              exp_neg_group<NPT>(xv, lv, av);
 #pragma unroll
               for (int k = 0; k < NPT; k++) accumulate_outflow(accj[k], pv[k], rn * occupation(av[k], sign), thr);
             }
@@ -268,15 +269,14 @@ cf_kernel(const HotParams hp)
               }
             }
           } else {
-            double xv[NPT], pv[NPT], sv[NPT], av[NPT]; bool any = false;
+            double xv[NPT], pv[NPT], sv[NPT], av[NPT]; bool lv[NPT]; bool any = false;
 #pragma unroll
             for (int k = 0; k < NPT; k++) {
               const double u = a - q[k];
-              const double x = sqrt_fast(fma(u, u, hz));
-              const bool alive = exp_finite(x);
-              any |= alive;
-              xv[k] = alive ? x : 1.0;
-              pv[k] = alive ? fma(w, pd[k], cpm) : 0.0;
+              xv[k] = sqrt_fast(fma(u, u, hz));
+              lv[k] = exp_finite(xv[k]);
+              any |= lv[k];
+              pv[k] = lv[k] ? fma(w, pd[k], cpm) : -0.0;
               double s = h0 + g0[k];
               s = fma(g2[k], h2, s);
               s = fma(-g1[k], h1, s);
@@ -284,7 +284,7 @@ cf_kernel(const HotParams hp)
               sv[k] = fma(K2 * u, u, s);
             }
             if (any) {
-              exp_neg_group<NPT>(xv, av);
+              exp_neg_group<NPT>(xv, lv, av);
 #pragma unroll
               for (int k = 0; k < NPT; k++) {
                 const double fa = occupation(av[k], sign);
@@ -322,7 +322,7 @@ cf_kernel(const HotParams hp)
               for (int k = 0; k < NPT; k++) {
                 const int n = ne + fm[k];
                 const double p = pe * fq[k];
-                av[k] = alive[k] ? exp_neg_fast(p, n) : 0.0;
+                av[k] = exp_neg_fast(p, n);
                 rare |= alive[k] && exp_neg_is_rare(n);
               }
               if (__builtin_expect(rare, 0)) {
@@ -331,12 +331,11 @@ cf_kernel(const HotParams hp)
               }
 #pragma unroll
               for (int k = 0; k < NPT; k++) {
-                const double x = alive[k] ? xs[k] : 1.0;
-                const double pds = alive[k] ? fma(w, pd[k], cpm) : 0.0;
+                const double pds = alive[k] ? fma(w, pd[k], cpm) : -0.0;
                 double s = h0 + g0[k];
                 s = fma(g2[k], h2, s);
                 s = fma(-g1[k], h1, s);
-                accumulate_outflow(accj[k], pds, distribution_from_a<MODEL>(av[k], x, s, K2, K3, sign, reg_thr), thr);
+                accumulate_outflow(accj[k], pds, distribution_from_a<MODEL>(av[k], xs[k], s, K2, K3, sign, reg_thr), thr);
               }
             }
           } else {
@@ -344,16 +343,15 @@ cf_kernel(const HotParams hp)
 #pragma unroll
             for (int k = 0; k < NPT; k++) { xs[k] = a - q[k]; alive[k] = exp_finite(xs[k]); any |= alive[k]; }
             if (any) {
-              double xv[NPT], sv[NPT], pv[NPT], fv[NPT];
+              double sv[NPT], pv[NPT], fv[NPT];
 #pragma unroll
               for (int k = 0; k < NPT; k++) {
-                xv[k] = alive[k] ? xs[k] : 1.0;                                // dead members: harmless argument, weight 0
-                pv[k] = alive[k] ? fma(w, pd[k], cpm) : 0.0;
+                pv[k] = alive[k] ? fma(w, pd[k], cpm) : -0.0;                  // -0.0 never passes the p.dsigma test
                 double s = h0 + g0[k];
                 s = fma(g2[k], h2, s);
                 sv[k] = fma(-g1[k], h1, s);
               }
-              distribution_group<MODEL, NPT>(xv, sv, K2, K3, sign, reg_thr, fv);
+              distribution_group<MODEL, NPT>(xs, alive, sv, K2, K3, sign, reg_thr, fv);
 #pragma unroll
               for (int k = 0; k < NPT; k++) accumulate_outflow(accj[k], pv[k], fv[k], thr);
             }
@@ -374,16 +372,16 @@ cf_kernel(const HotParams hp)
           lA[k] = exp_finite(xA[k]); lB[k] = exp_finite(xB[k]); any |= lA[k] | lB[k];
         }
         if (any) {
-          double xv[2 * NPT], sv[2 * NPT], pv[2 * NPT], fv[2 * NPT];
+          double xv[2 * NPT], sv[2 * NPT], pv[2 * NPT], fv[2 * NPT]; bool lv[2 * NPT];
 #pragma unroll
           for (int k = 0; k < NPT; k++) {
-            xv[k] = lA[k] ? xA[k] : 1.0; xv[NPT + k] = lB[k] ? xB[k] : 1.0;
-            pv[k] = lA[k] ? fma(wA, pd[k], cA) : 0.0; pv[NPT + k] = lB[k] ? fma(wB, pd[k], cB) : 0.0;
+            xv[k] = xA[k]; xv[NPT + k] = xB[k]; lv[k] = lA[k]; lv[NPT + k] = lB[k];
+            pv[k] = lA[k] ? fma(wA, pd[k], cA) : -0.0; pv[NPT + k] = lB[k] ? fma(wB, pd[k], cB) : -0.0;
             double s0 = h0A + g0[k], s1 = h0B + g0[k];
             s0 = fma(g2[k], h2A, s0); s1 = fma(g2[k], h2B, s1);
             sv[k] = fma(-g1[k], h1A, s0); sv[NPT + k] = fma(-g1[k], h1B, s1);
           }
-          distribution_group<MODEL, 2 * NPT>(xv, sv, K2, K3, sign, reg_thr, fv);
+          distribution_group<MODEL, 2 * NPT>(xv, lv, sv, K2, K3, sign, reg_thr, fv);
 #pragma unroll
           for (int k = 0; k < 2 * NPT; k++) accumulate_outflow(accj[k], pv[k], fv[k], thr);
         }
@@ -449,7 +447,7 @@ cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, i
 struct Shape { int nyt, npt, ct, minb, sb; };
 static const Shape kShapes3D[] = {
   {7, 1, 16, 6, 0}, {7, 3, 16, 3, 0}, {7, 2, 16, 4, 0}, {7, 4, 16, 3, 0}, {7, 2, 16, 5, 0}, {3, 6, 16, 3, 0}, {7, 6, 16, 2, 0}, {7, 3, 16, 4, 0},
-  {7, 3, 16, 4, 3}, {7, 2, 16, 4, 1}, {7, 3, 16, 3, 3}, {7, 3, 16, 4, 1}, {7, 3, 16, 3, 1}, {7, 4, 16, 3, 3}, {7, 2, 16, 6, 1}, {7, 6, 16, 2, 3}};
+  {7, 3, 16, 4, 3}, {3, 4, 16, 4, 3}, {7, 3, 16, 3, 3}, {7, 3, 16, 4, 1}, {7, 3, 16, 3, 1}, {3, 4, 16, 5, 3}, {7, 2, 16, 6, 1}, {3, 6, 16, 4, 3}};
 static const Shape kShapes2D[] = {
   {1, 3, 1, 4, 0}, {1, 4, 1, 4, 0}, {1, 6, 1, 3, 0}, {1, 8, 1, 3, 0}, {1, 2, 1, 5, 0}, {1, 12, 1, 2, 0}, {1, 4, 1, 3, 0}, {1, 1, 1, 6, 0},
   {1, 6, 1, 3, 3}, {1, 3, 1, 4, 1}, {1, 4, 1, 4, 3}, {1, 4, 1, 3, 1}, {1, 6, 1, 3, 1}, {1, 8, 1, 3, 3}, {1, 3, 1, 5, 1}, {1, 12, 1, 2, 3}};
@@ -523,13 +521,13 @@ static cudaError_t launch_model(const HotParams &hp, int variant, cudaStream_t s
   if constexpr (TUNE) {
     switch (variant) {
       case 8: return launch_one<MODEL, 7, 3, false, 4, 3>(hp, st, smem_out);
-      case 9: return launch_one<MODEL, 7, 2, false, 4, 1>(hp, st, smem_out);
+      case 9: return launch_one<MODEL, 3, 4, false, 4, 3>(hp, st, smem_out);
       case 10: return launch_one<MODEL, 7, 3, false, 3, 3>(hp, st, smem_out);
       case 11: return launch_one<MODEL, 7, 3, false, 4, 1>(hp, st, smem_out);
       case 12: return launch_one<MODEL, 7, 3, false, 3, 1>(hp, st, smem_out);
-      case 13: return launch_one<MODEL, 7, 4, false, 3, 3>(hp, st, smem_out);
+      case 13: return launch_one<MODEL, 3, 4, false, 5, 3>(hp, st, smem_out);
       case 14: return launch_one<MODEL, 7, 2, false, 6, 1>(hp, st, smem_out);
-      case 15: return launch_one<MODEL, 7, 6, false, 2, 3>(hp, st, smem_out);
+      case 15: return launch_one<MODEL, 3, 6, false, 4, 3>(hp, st, smem_out);
       default: break;
     }
   }
