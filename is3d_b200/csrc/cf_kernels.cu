@@ -447,7 +447,7 @@ cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, i
 struct Shape { int nyt, npt, ct, minb, sb; };
 static const Shape kShapes3D[] = {
   {7, 1, 16, 6, 0}, {7, 3, 16, 3, 0}, {7, 2, 16, 4, 0}, {7, 4, 16, 3, 0}, {7, 2, 16, 5, 0}, {3, 6, 16, 3, 0}, {7, 6, 16, 2, 0}, {7, 3, 16, 4, 0},
-  {7, 3, 16, 4, 3}, {3, 4, 16, 4, 3}, {7, 3, 16, 3, 3}, {7, 3, 16, 4, 1}, {7, 3, 16, 3, 1}, {3, 4, 16, 5, 3}, {7, 2, 16, 6, 1}, {3, 6, 16, 4, 3}};
+  {7, 3, 16, 4, 3}, {7, 3, 16, 5, 1}, {7, 3, 16, 3, 3}, {7, 3, 16, 4, 1}, {7, 3, 16, 3, 1}, {7, 4, 16, 4, 1}, {7, 2, 16, 6, 1}, {7, 3, 16, 4, 2}};
 static const Shape kShapes2D[] = {
   {1, 3, 1, 4, 0}, {1, 4, 1, 4, 0}, {1, 6, 1, 3, 0}, {1, 8, 1, 3, 0}, {1, 2, 1, 5, 0}, {1, 12, 1, 2, 0}, {1, 4, 1, 3, 0}, {1, 1, 1, 6, 0},
   {1, 6, 1, 3, 3}, {1, 3, 1, 4, 1}, {1, 4, 1, 4, 3}, {1, 4, 1, 3, 1}, {1, 6, 1, 3, 1}, {1, 8, 1, 3, 3}, {1, 3, 1, 5, 1}, {1, 12, 1, 2, 3}};
@@ -521,13 +521,13 @@ static cudaError_t launch_model(const HotParams &hp, int variant, cudaStream_t s
   if constexpr (TUNE) {
     switch (variant) {
       case 8: return launch_one<MODEL, 7, 3, false, 4, 3>(hp, st, smem_out);
-      case 9: return launch_one<MODEL, 3, 4, false, 4, 3>(hp, st, smem_out);
+      case 9: return launch_one<MODEL, 7, 3, false, 5, 1>(hp, st, smem_out);
       case 10: return launch_one<MODEL, 7, 3, false, 3, 3>(hp, st, smem_out);
       case 11: return launch_one<MODEL, 7, 3, false, 4, 1>(hp, st, smem_out);
       case 12: return launch_one<MODEL, 7, 3, false, 3, 1>(hp, st, smem_out);
-      case 13: return launch_one<MODEL, 3, 4, false, 5, 3>(hp, st, smem_out);
+      case 13: return launch_one<MODEL, 7, 4, false, 4, 1>(hp, st, smem_out);
       case 14: return launch_one<MODEL, 7, 2, false, 6, 1>(hp, st, smem_out);
-      case 15: return launch_one<MODEL, 3, 6, false, 4, 3>(hp, st, smem_out);
+      case 15: return launch_one<MODEL, 7, 3, false, 4, 2>(hp, st, smem_out);
       default: break;
     }
   }
