@@ -188,7 +188,8 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
   if (!vah && (fl->df_mode < 1 || fl->df_mode > 4)) return fail(IS3D_ERR_ARGUMENT, "df_mode must be 1..4");
   if (!vah && (!df || df->n_T < 3 || !df->T)) return fail(IS3D_ERR_ARGUMENT, "delta-f coefficient tables missing");
   const bool feqmod = !vah && (fl->df_mode == 3 || fl->df_mode == 4);
-  const int model = vah ? M_VAH : (fl->df_mode == 1 ? M_LIN14 : fl->df_mode == 2 ? M_LINCE : M_FEQMOD);
+  const bool ideal = !vah && (fl->df_mode == 1 || fl->df_mode == 2) && !fl->include_shear_deltaf && !fl->include_bulk_deltaf;
+  const int model = vah ? M_VAH : ideal ? M_IDEAL : (fl->df_mode == 1 ? M_LIN14 : fl->df_mode == 2 ? M_LINCE : M_FEQMOD);
   if (!vah) {
     if (fl->df_mode == 1 && (!df->c0 || !df->c2)) return fail(IS3D_ERR_ARGUMENT, "df_mode 1 needs the c0 and c2 tables");
     if ((fl->df_mode == 2 || fl->df_mode == 3) && (!df->F || !df->betabulk || !df->betapi)) return fail(IS3D_ERR_ARGUMENT, "df_mode 2/3 need the F, betabulk and betapi tables");
@@ -212,7 +213,7 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
   // tile_variant: 0 = model default (tuned on B200, see profiles/), k > 0 = table entry k - 1 (tuning / tests)
   int variant;
   if (opt.tile_variant >= 1 && opt.tile_variant <= 16) variant = opt.tile_variant - 1;
-  else if (dim2_early) variant = (model == M_FEQMOD || model == M_VAH) ? 12 : 10;
+  else if (dim2_early) variant = (model == M_FEQMOD || model == M_VAH) ? 12 : (model == M_IDEAL ? 13 : 10);
   else variant = (model == M_FEQMOD || model == M_VAH) ? 12 : 11;
   int nyt, npt, ct;
   hot_variant_shape(variant, L.dim2, &nyt, &npt, &ct);

@@ -55,7 +55,8 @@ enum Model {
   M_LINCE = 2,      // f_eq (1 + df), Chapman-Enskog       (:313-321, also the df_mode 3 breakdown branch :835-857)
   M_FEQMOD = 3,     // modified equilibrium, Mike / Jonah  (:878-928)
   M_JONAHLIN = 4,   // Jonah's linearised df, breakdown branch of df_mode 4 (:858-876)
-  M_VAH = 5         // anisotropic f_a (1 + df~), PL matching (:2297-2349)
+  M_VAH = 5,        // anisotropic f_a (1 + df~), PL matching (:2297-2349)
+  M_IDEAL = 6       // f_eq only: df_mode 1/2 with include_shear_deltaf = include_bulk_deltaf = 0 (df = 0 exactly, BASELINE cfg2)
 };
 
 struct HotParams {

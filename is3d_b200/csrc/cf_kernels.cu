@@ -27,6 +27,7 @@ __device__ __forceinline__ double occupation(double a, double sign) { return a *
 template <int MODEL>
 __device__ __forceinline__ double distribution(double x, double s, double K2, double K3, double sign, int reg_thr)
 {
+  if (MODEL == M_IDEAL) return occupation(exp_neg(x), sign);      // df = 0: f = f_eq (1 + 0)
   double dfs;
   if (MODEL == M_LIN14) dfs = fma(K2 * x, x, s);               // + Pi bulk2 (u.p)^2
   else dfs = fma(s, rcp_fast(x), K2 * x);                      // [..]/(u.p) + (..)(u.p)
@@ -63,6 +64,7 @@ __device__ __forceinline__ void exp_neg_group(const double (&x)[N], const bool (
 template <int MODEL>
 __device__ __forceinline__ double distribution_from_a(double a, double x, double s, double K2, double K3, double sign, int reg_thr)
 {
+  if (MODEL == M_IDEAL) return occupation(a, sign);
   double dfs;
   if (MODEL == M_LIN14) dfs = fma(K2 * x, x, s);
   else dfs = fma(s, rcp_fast(x), K2 * x);
@@ -85,7 +87,8 @@ __device__ __forceinline__ void distribution_group(const double (&x)[N], const b
   for (int i = 0; i < N; i++) {
     exp_neg_poly(x[i], p[i], n[i]);
     rare |= alive[i] && exp_neg_is_rare(n[i]);
-    if (MODEL == M_LIN14) dfs[i] = fma(K2 * x[i], x[i], s[i]);
+    if (MODEL == M_IDEAL) dfs[i] = 0.0;
+    else if (MODEL == M_LIN14) dfs[i] = fma(K2 * x[i], x[i], s[i]);
     else dfs[i] = fma(s[i], rcp_fast(x[i]), K2 * x[i]);
   }
 #pragma unroll
@@ -97,6 +100,7 @@ __device__ __forceinline__ void distribution_group(const double (&x)[N], const b
 #pragma unroll
   for (int i = 0; i < N; i++) {
     const double feq = occupation(a[i], sign);
+    if (MODEL == M_IDEAL) { f[i] = feq; continue; }
     const double feqbar = fma(-sign, feq, 1.0);
     double df = (MODEL == M_JONAHLIN) ? fma(feqbar, dfs[i], K3) : feqbar * dfs[i];
     df = clamp_unit(df, reg_thr);
@@ -542,6 +546,7 @@ cudaError_t launch_hot(int model, const HotParams &hp, int variant, cudaStream_t
     case M_FEQMOD: return launch_model<M_FEQMOD>(hp, variant, st, smem_out);
     case M_JONAHLIN: return launch_model<M_JONAHLIN>(hp, variant, st, smem_out);
     case M_VAH: return launch_model<M_VAH>(hp, variant, st, smem_out);
+    case M_IDEAL: return launch_model<M_IDEAL>(hp, variant, st, smem_out);
     default: return cudaErrorInvalidValue;
   }
 }
