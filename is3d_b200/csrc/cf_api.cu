@@ -214,7 +214,7 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
   int variant;
   if (opt.tile_variant >= 1 && opt.tile_variant <= 16) variant = opt.tile_variant - 1;
   else if (dim2_early) variant = (model == M_FEQMOD || model == M_VAH) ? 12 : (model == M_IDEAL ? 13 : 10);
-  else variant = (model == M_FEQMOD || model == M_VAH) ? 12 : 11;
+  else variant = (model == M_FEQMOD || model == M_VAH) ? 12 : 9;
   int nyt, npt, ct;
   hot_variant_shape(variant, L.dim2, &nyt, &npt, &ct);
   L.nst = dim2 ? L.n_slots : nyt;

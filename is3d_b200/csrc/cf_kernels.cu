@@ -390,9 +390,44 @@ cf_kernel(const HotParams hp)
           for (int k = 0; k < 2 * NPT; k++) accumulate_outflow(accj[k], pv[k], fv[k], thr);
         }
       };
+      // SB == 4 (linear models, 3+1D): like SB == 1, but the aliveness test of slot j + 1 is issued before slot j is
+      // evaluated, so that the skip branch of the next slot never waits for its predicate chain (DMUL, DADD, 2 ISETP)
+      auto probe = [&](int j, double (&x)[NPT], bool (&l)[NPT], bool &any) {
+        const double a = mT * Ys[(c * nst + j) * RY];
+        any = false;
+#pragma unroll
+        for (int k = 0; k < NPT; k++) { x[k] = a - q[k]; l[k] = exp_finite(x[k]); any |= l[k]; }
+      };
+      auto eval_probed = [&](int j, const double (&x)[NPT], const bool (&l)[NPT], double *accj) {
+        const double2 *yr = reinterpret_cast<const double2 *>(Ys + (c * nst + j) * RY);
+        const double2 v0 = yr[0], v1 = yr[1], v2 = yr[2];
+        const double cpm = mT * v0.y, h0 = mT2 * v1.x, h1 = mT * v1.y, h2 = mT * v2.x, w = v2.y;
+        double sv[NPT], pv[NPT], fv[NPT];
+#pragma unroll
+        for (int k = 0; k < NPT; k++) {
+          pv[k] = l[k] ? fma(w, pd[k], cpm) : -0.0;
+          double s = h0 + g0[k];
+          s = fma(g2[k], h2, s);
+          sv[k] = fma(-g1[k], h1, s);
+        }
+        distribution_group<MODEL, NPT>(x, l, sv, K2, K3, sign, reg_thr, fv);
+#pragma unroll
+        for (int k = 0; k < NPT; k++) accumulate_outflow(accj[k], pv[k], fv[k], thr);
+      };
       if (DIM2) {
 #pragma unroll 2
         for (int j = 0; j < nst; j++) slot(j, acc);
+      } else if (SB == 4 && MODEL != M_FEQMOD && MODEL != M_VAH) {
+        double xa[NPT], xb[NPT]; bool la[NPT], lb[NPT]; bool anya, anyb = false;
+        probe(0, xa, la, anya);
+#pragma unroll
+        for (int j = 0; j < NYT; j++) {
+          if (j + 1 < NYT) probe(j + 1, xb, lb, anyb);
+          if (anya) eval_probed(j, xa, la, acc + j * NPT);
+#pragma unroll
+          for (int k = 0; k < NPT; k++) { xa[k] = xb[k]; la[k] = lb[k]; }
+          anya = anyb;
+        }
       } else if (SB == 2 && MODEL != M_FEQMOD && MODEL != M_VAH) {
 #pragma unroll
         for (int j = 0; j + 1 < NYT; j += 2) slot_pair(j, acc + j * NPT);
@@ -451,7 +486,7 @@ cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, i
 struct Shape { int nyt, npt, ct, minb, sb; };
 static const Shape kShapes3D[] = {
   {7, 1, 16, 6, 0}, {7, 3, 16, 3, 0}, {7, 2, 16, 4, 0}, {7, 4, 16, 3, 0}, {7, 2, 16, 5, 0}, {3, 6, 16, 3, 0}, {7, 6, 16, 2, 0}, {7, 3, 16, 4, 0},
-  {7, 3, 16, 4, 3}, {7, 3, 16, 5, 1}, {7, 3, 16, 3, 3}, {7, 3, 16, 4, 1}, {7, 3, 16, 3, 1}, {7, 4, 16, 4, 1}, {7, 2, 16, 6, 1}, {7, 3, 16, 4, 2}};
+  {7, 3, 16, 4, 3}, {7, 3, 16, 3, 4}, {7, 3, 16, 3, 3}, {7, 3, 16, 4, 1}, {7, 3, 16, 3, 1}, {7, 4, 16, 4, 1}, {7, 2, 16, 6, 1}, {7, 3, 16, 4, 4}};
 static const Shape kShapes2D[] = {
   {1, 3, 1, 4, 0}, {1, 4, 1, 4, 0}, {1, 6, 1, 3, 0}, {1, 8, 1, 3, 0}, {1, 2, 1, 5, 0}, {1, 12, 1, 2, 0}, {1, 4, 1, 3, 0}, {1, 1, 1, 6, 0},
   {1, 6, 1, 3, 3}, {1, 3, 1, 4, 1}, {1, 4, 1, 4, 3}, {1, 4, 1, 3, 1}, {1, 6, 1, 3, 1}, {1, 8, 1, 3, 3}, {1, 3, 1, 5, 1}, {1, 12, 1, 2, 3}};
@@ -525,13 +560,13 @@ static cudaError_t launch_model(const HotParams &hp, int variant, cudaStream_t s
   if constexpr (TUNE) {
     switch (variant) {
       case 8: return launch_one<MODEL, 7, 3, false, 4, 3>(hp, st, smem_out);
-      case 9: return launch_one<MODEL, 7, 3, false, 5, 1>(hp, st, smem_out);
+      case 9: return launch_one<MODEL, 7, 3, false, 3, 4>(hp, st, smem_out);
       case 10: return launch_one<MODEL, 7, 3, false, 3, 3>(hp, st, smem_out);
       case 11: return launch_one<MODEL, 7, 3, false, 4, 1>(hp, st, smem_out);
       case 12: return launch_one<MODEL, 7, 3, false, 3, 1>(hp, st, smem_out);
       case 13: return launch_one<MODEL, 7, 4, false, 4, 1>(hp, st, smem_out);
       case 14: return launch_one<MODEL, 7, 2, false, 6, 1>(hp, st, smem_out);
-      case 15: return launch_one<MODEL, 7, 3, false, 4, 2>(hp, st, smem_out);
+      case 15: return launch_one<MODEL, 7, 3, false, 4, 4>(hp, st, smem_out);
       default: break;
     }
   }
