@@ -32,7 +32,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOPS_PER_EVAL = {1: 85.0, 2: 87.0, 3: 140.0, 4: 140.0}
+FLOPS_PER_EVAL = {1: 85.0, 2: 87.0, 3: 140.0, 4: 140.0, 5: 94.0}     # SURVEY.md section 8(d); 5 = anisotropic PL kernel
 IDEAL_FLOPS = 29.0
 
 WORKLOADS = {
@@ -41,6 +41,7 @@ WORKLOADS = {
     "cfg4ce": (1_000_000, 3, 2, "chosen_urqmd", True, "cfg4: 1M-cell 3+1D viscous surface, full PDG, Chapman-Enskog df"),
     "cfg4mike": (1_000_000, 3, 3, "chosen_urqmd", True, "cfg4: 1M-cell 3+1D viscous surface, full PDG, feqmod (Mike)"),
     "cfg4jonah": (1_000_000, 3, 4, "chosen_urqmd", True, "cfg4: 1M-cell 3+1D viscous surface, full PDG, feqmod (Jonah)"),
+    "cfg5": (1_000_000, 3, 5, "chosen_urqmd", True, "cfg5: 1M-cell 3+1D anisotropic-hydro surface (PL matching), full PDG, residual 14-moment df"),
     "cfg2": (100_000, 2, 1, "chosen_pikp", False, "cfg2: 100k-cell boost-invariant surface, pi/K/p, ideal f_eq, 241-point eta quadrature"),
 }
 
@@ -201,15 +202,23 @@ def main():
     n_cells = args.cells or n_full
     fx = tables.load_fixture()
     sp = tables.species(fx, 1, chosen); g = tables.grid(fx); tab = tables.df_tables(fx, 1); gla = tables.laguerre(fx)
-    fl = tables.flags(df_mode=dfm, dimension=dim, include_bulk=int(viscous), include_shear=int(viscous))
-    cols = synthetic.surface_vh(n_cells, synthetic.SEEDS["cfg3" if dim == 3 else "cfg2"], three_d=(dim == 3), viscous=viscous)
-    cells = synthetic.columns_to_cells(cols, 1)
+    vah = (dfm == 5)
+    fl = tables.flags(df_mode=(1 if vah else dfm), dimension=dim, include_bulk=int(viscous), include_shear=int(viscous))
+    if vah:
+        fl["mode"] = 2
+        cols = synthetic.surface_vah(n_cells, synthetic.SEEDS["cfg5"])
+        cells = api.vah_cells(cols, fx)
+    else:
+        cols = synthetic.surface_vh(n_cells, synthetic.SEEDS["cfg3" if dim == 3 else "cfg2"], three_d=(dim == 3), viscous=viscous)
+        cells = synthetic.columns_to_cells(cols, 1)
     del cols
     if dfm == 4:                                   # global lambda/z tables at the surface-average temperature, before sharding
         pdg = tables.pdg_table(fx, 1)
         avg = api.surface_averages(cells)
         tab.update(api.jonah_tables(pdg["mass"], pdg["gspin"].astype(float), pdg["sign"].astype(float), avg[0], gla))
     keys = ["tau", "eta", "dat", "dax", "day", "dan", "ux", "uy", "un", "T", "P", "E", "pixx", "pixy", "pixn", "piyy", "piyn", "bulkPi"]
+    if vah:
+        keys += ["pitt", "pitx", "pity", "pitn", "pinn", "Wx", "Wy", "Lambda", "aL", "c0", "c1", "c2", "c3", "c4"]
     lo, hi = distributed.shard_bounds(n_cells, rank, world)
     # pinned host copies of this rank's shard (e2e leg) and device-resident copies (value leg)
     host = {k: torch.from_numpy(np.ascontiguousarray(cells[k][lo:hi])).pin_memory() for k in keys}
@@ -319,6 +328,8 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
+            if vah:
+                raise RuntimeError("the reference cannot run this configuration: its anisotropic kernel is dead code (SURVEY R1)")
             r = reference_sample(args.workload)
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:          # the baseline is a reported number, never a reason to lose the GPU measurement

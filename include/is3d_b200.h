@@ -137,6 +137,13 @@ int is3d_b200_surface_averages(const is3d_surface *surface, double *out5);
 int is3d_b200_jonah_tables(int32_t n_particles, const double *mass, const double *degeneracy, const double *sign, double T_avg,
                            int32_t n_points, const double *root2, const double *weight2,
                            double *x301, double *lambda2_301, double *z301, double *bulkPi_over_Peq_max);
+/* Anisotropic hydro, in-memory callers: alpha_L and Lambda [GeV] from the surface file's T, P, PL columns [fm units]
+ * (readindata.cpp:905-918), and the per-cell c0..c4 from the (Lambda [fm^-1], alpha_L) tables, each table given as
+ * c[iL * naL + iaL] with the values of deltaf_coefficients/vah/c{k}_vah1.dat (src/cuda/deltafReader.cu:192-277). */
+int is3d_b200_vah_anisotropy(int64_t n, const double *T_fm, const double *P_fm, const double *PL_fm, double *aL_out, double *Lambda_GeV_out);
+int is3d_b200_vah_coefficients(int32_t nL, int32_t naL, const double *L_fm, const double *aL_grid, const double *c0, const double *c1,
+                               const double *c2, const double *c3, const double *c4, int64_t n, const double *Lambda_GeV,
+                               const double *aL, double *o0, double *o1, double *o2, double *o3, double *o4);
 /* Writers only: produce the results/ files of `workdir` from a spectra array in the reference layout. */
 int is3d_b200_write_results(const char *workdir, const double *dN, int64_t n);
 /* Host-layer inspection without GPU work: dumps what the readers derived (named double records) to out_path. */

@@ -142,6 +142,30 @@ def jonah_tables(pdg_mass, pdg_degeneracy, pdg_sign, T_avg, laguerre):
     return dict(jonah_x=x, jonah_lambda2=l2, jonah_z=z, bulkPi_over_Peq_max=mx.value)
 
 
+def vah_cells(columns, fx):
+    """Mode-2 (31 column) surface -> SoA dict incl. alpha_L, Lambda and per-cell c0..c4 (C++ host layer, in memory)."""
+    from . import synthetic
+    cells = synthetic.columns_to_cells(columns, 2)
+    a = np.ascontiguousarray(columns, dtype=np.float64)
+    n = len(a)
+    m = _Marshal(False)
+    aL = np.zeros(n); Lam = np.zeros(n)
+    f = lib().is3d_b200_vah_anisotropy
+    f.argtypes = [C.c_int64, _D, _D, _D, _D, _D]
+    _check(f(n, m.host(a[:, 13]), m.host(a[:, 14]), m.host(a[:, 15]), aL.ctypes.data_as(_D), Lam.ctypes.data_as(_D)))
+    nL, naL = int(fx["df_vah/nL"]), int(fx["df_vah/naL"])
+    Lg = fx["df_vah/L_col"][:nL]; ag = fx["df_vah/aL_col"][::nL]
+    tabs = [np.ascontiguousarray(fx["df_vah/c%d" % k].reshape(naL, nL).T) for k in range(5)]      # -> [iL][iaL]
+    out = [np.zeros(n) for _ in range(5)]
+    g = lib().is3d_b200_vah_coefficients
+    g.argtypes = [C.c_int32, C.c_int32, _D, _D, _D, _D, _D, _D, _D, C.c_int64, _D, _D, _D, _D, _D, _D, _D]
+    _check(g(nL, naL, m.host(Lg), m.host(ag), *[m.host(t) for t in tabs], n, m.host(Lam), m.host(aL), *[o.ctypes.data_as(_D) for o in out]))
+    cells["aL"] = aL; cells["Lambda"] = Lam
+    for k in range(5):
+        cells["c%d" % k] = out[k]
+    return cells
+
+
 def _is_torch(x):
     return type(x).__module__.startswith("torch")
 

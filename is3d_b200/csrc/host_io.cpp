@@ -436,39 +436,52 @@ double R200(double aL)
   return aL * t200;
 }
 
-bool fill_vah_coefficients(const std::string &workdir, SurfaceData *s, std::string *err)
+// bilinear lookup of one cell's c0..c4 in the (Lambda [fm^-1], alpha_L) tables; tables are [iL * naL + iaL]
+bool vah_lookup(int nL, int naL, const double *L, const double *aLv, const double *const c[5], double Lam_fm, double a, double out[5])
 {
-  int nL = 0, naL = 0;
-  std::vector<double> L, aLv, c[5];
+  // first table cell with Lambda < L[i1] and aL < aL[i2] (i1, i2 >= 1), as the loops of src/cuda/deltafReader.cu:222-277 find it
+  int i2 = 1; while (i2 < naL && !(a < aLv[i2])) i2++;
+  int i1 = 1; while (i1 < nL && !(Lam_fm < L[i1])) i1++;
+  if (i1 >= nL || i2 >= naL) return false;
+  const double hbarC3 = kHbarC * kHbarC * kHbarC;
+  const double L1 = L[i1 - 1], L2 = L[i1], a1 = aLv[i2 - 1], a2 = aLv[i2];
+  for (int k = 0; k < 5; k++) {
+    const double f11 = c[k][(size_t)(i1 - 1) * naL + (i2 - 1)], f21 = c[k][(size_t)i1 * naL + (i2 - 1)];
+    const double f12 = c[k][(size_t)(i1 - 1) * naL + i2], f22 = c[k][(size_t)i1 * naL + i2];
+    const double v = ((f11 * (L2 - Lam_fm) + f21 * (Lam_fm - L1)) * (a2 - a) + (f12 * (L2 - Lam_fm) + f22 * (Lam_fm - L1)) * (a - a1)) / ((a2 - a1) * (L2 - L1));
+    out[k] = v / hbarC3;
+  }
+  return true;
+}
+
+bool read_vah_tables(const std::string &workdir, VahTables *t, std::string *err)
+{
   for (int k = 0; k < 5; k++) {
     const std::string path = workdir + "/deltaf_coefficients/vah/c" + std::to_string(k) + "_vah1.dat";
     FILE *f = std::fopen(path.c_str(), "r");
     if (!f) { if (err) *err = "couldn't open " + path; return false; }
     char header[300];
-    if (std::fscanf(f, "%d\n%d\n", &nL, &naL) != 2 || !std::fgets(header, 100, f)) { std::fclose(f); if (err) *err = "bad header in " + path; return false; }
-    L.assign(nL, 0.0); aLv.assign(naL, 0.0); c[k].assign((size_t)nL * naL, 0.0);
-    for (int i2 = 0; i2 < naL; i2++)
-      for (int i1 = 0; i1 < nL; i1++)
-        if (std::fscanf(f, "%lf\t\t%lf\t\t%lf\n", &L[i1], &aLv[i2], &c[k][(size_t)i1 * naL + i2]) != 3) { std::fclose(f); if (err) *err = "short table " + path; return false; }
+    if (std::fscanf(f, "%d\n%d\n", &t->nL, &t->naL) != 2 || !std::fgets(header, 100, f)) { std::fclose(f); if (err) *err = "bad header in " + path; return false; }
+    t->L.assign(t->nL, 0.0); t->aL.assign(t->naL, 0.0); t->c[k].assign((size_t)t->nL * t->naL, 0.0);
+    for (int i2 = 0; i2 < t->naL; i2++)
+      for (int i1 = 0; i1 < t->nL; i1++)
+        if (std::fscanf(f, "%lf\t\t%lf\t\t%lf\n", &t->L[i1], &t->aL[i2], &t->c[k][(size_t)i1 * t->naL + i2]) != 3) { std::fclose(f); if (err) *err = "short table " + path; return false; }
     std::fclose(f);
   }
-  const double hbarC3 = kHbarC * kHbarC * kHbarC;
+  return true;
+}
+
+bool fill_vah_coefficients(const std::string &workdir, SurfaceData *s, std::string *err)
+{
+  VahTables t;
+  if (!read_vah_tables(workdir, &t, err)) return false;
+  const double *c[5] = {t.c[0].data(), t.c[1].data(), t.c[2].data(), t.c[3].data(), t.c[4].data()};
   for (int64_t i = 0; i < s->n; i++) {
-    const double a = s->aL[i], Lam = s->Lambda[i] / kHbarC;
-    // first table cell with Lambda < L[i1] and aL < aL[i2] (i1, i2 >= 1)
-    int i2 = 1; while (i2 < naL && !(a < aLv[i2])) i2++;
-    int i1 = 1; while (i1 < nL && !(Lam < L[i1])) i1++;
-    if (i1 >= nL || i2 >= naL) {
+    double out[5];
+    if (!vah_lookup(t.nL, t.naL, t.L.data(), t.aL.data(), c, s->Lambda[i] / kHbarC, s->aL[i], out)) {
       if (err) *err = "cell " + std::to_string(i) + ": (Lambda, alpha_L) outside the vah coefficient table"; return false;
     }
-    const double L1 = L[i1 - 1], L2 = L[i1], a1 = aLv[i2 - 1], a2 = aLv[i2];
-    double *dst[5] = {&s->c0[i], &s->c1[i], &s->c2[i], &s->c3[i], &s->c4[i]};
-    for (int k = 0; k < 5; k++) {
-      const double f11 = c[k][(size_t)(i1 - 1) * naL + (i2 - 1)], f21 = c[k][(size_t)i1 * naL + (i2 - 1)];
-      const double f12 = c[k][(size_t)(i1 - 1) * naL + i2], f22 = c[k][(size_t)i1 * naL + i2];
-      double v = ((f11 * (L2 - Lam) + f21 * (Lam - L1)) * (a2 - a) + (f12 * (L2 - Lam) + f22 * (Lam - L1)) * (a - a1)) / ((a2 - a1) * (L2 - L1));
-      *dst[k] = v / hbarC3;
-    }
+    s->c0[i] = out[0]; s->c1[i] = out[1]; s->c2[i] = out[2]; s->c3[i] = out[3]; s->c4[i] = out[4];
   }
   return true;
 }

@@ -71,6 +71,9 @@ void compute_jonah_tables(const std::vector<Particle> &pdg, double T, const Lagu
 
 // anisotropic-hydro per-cell coefficients: bilinear lookup in deltaf_coefficients/vah/c{0..4}_vah1.dat
 // (only specification: reference src/cuda/deltafReader.cu:192-277)
+struct VahTables { int nL = 0, naL = 0; std::vector<double> L, aL, c[5]; };     // c[k][iL * naL + iaL]
+bool read_vah_tables(const std::string &workdir, VahTables *out, std::string *err);
+bool vah_lookup(int nL, int naL, const double *L, const double *aL_grid, const double *const c[5], double Lambda_fm, double aL, double out[5]);
 bool fill_vah_coefficients(const std::string &workdir, SurfaceData *surf, std::string *err);
 double aL_fit(double pl_over_peq);    // arsenal.cpp:999-1028
 double R200(double aL);               // arsenal.cpp:1031-1066

@@ -370,6 +370,38 @@ extern "C" int is3d_b200_surface_averages(const is3d_surface *sf, double *out5)
   return IS3D_OK;
 }
 
+// Anisotropic-hydro helpers for in-memory callers: (alpha_L, Lambda) from (T, P, PL) in the file's fm units as
+// FO_data_reader::read_surf_VAH_PLMatch infers them (readindata.cpp:905-918), and the per-cell c0..c4 lookup.
+extern "C" int is3d_b200_vah_anisotropy(int64_t n, const double *T_fm, const double *P_fm, const double *PL_fm, double *aL_out, double *Lambda_GeV_out)
+{
+  if (n < 0 || !T_fm || !P_fm || !PL_fm || !aL_out || !Lambda_GeV_out) return IS3D_ERR_ARGUMENT;
+  for (int64_t i = 0; i < n; i++) {
+    if (!((PL_fm[i] / P_fm[i]) < 3.0)) { g_host_error = "pl is too large, stopping anisotropic variables"; return IS3D_ERR_TABLE_RANGE; }
+    const double a = aL_fit(PL_fm[i] / P_fm[i]);
+    aL_out[i] = a;
+    Lambda_GeV_out[i] = (T_fm[i] / std::pow(0.5 * a * R200(a), 0.25)) * 0.197327053;
+  }
+  return IS3D_OK;
+}
+
+extern "C" int is3d_b200_vah_coefficients(int32_t nL, int32_t naL, const double *L_fm, const double *aL_grid, const double *c0, const double *c1,
+                                          const double *c2, const double *c3, const double *c4, int64_t n, const double *Lambda_GeV,
+                                          const double *aL, double *o0, double *o1, double *o2, double *o3, double *o4)
+{
+  if (nL < 2 || naL < 2 || !L_fm || !aL_grid || !c0 || !c1 || !c2 || !c3 || !c4 || n < 0 || !Lambda_GeV || !aL) return IS3D_ERR_ARGUMENT;
+  const double *c[5] = {c0, c1, c2, c3, c4};
+  double *o[5] = {o0, o1, o2, o3, o4};
+  for (int64_t i = 0; i < n; i++) {
+    double out[5];
+    if (!vah_lookup(nL, naL, L_fm, aL_grid, c, Lambda_GeV[i] / 0.197327053, aL[i], out)) {
+      g_host_error = "cell " + std::to_string(i) + ": (Lambda, alpha_L) outside the vah coefficient table";
+      return IS3D_ERR_TABLE_RANGE;
+    }
+    for (int k = 0; k < 5; k++) o[k][i] = out[k];
+  }
+  return IS3D_OK;
+}
+
 extern "C" int is3d_b200_jonah_tables(int32_t n_particles, const double *mass, const double *degeneracy, const double *sign, double T_avg,
                                       int32_t n_points, const double *root2, const double *weight2,
                                       double *x301, double *lambda2_301, double *z301, double *mx)

@@ -248,3 +248,18 @@ def test_other_surface_formats_against_reference(fx, mode, dimension):
     dN, skipped, _ = cfo.smooth(tables.flags(df_mode=1, dimension=dimension), cells, sp, g, tab, None)
     assert len(cells["tau"]) == 12 and skipped == 0
     assert np.array_equal(dN, ref)
+
+
+def test_vah_in_memory_helpers(fx):
+    """is3d_b200_vah_anisotropy / is3d_b200_vah_coefficients give what the file path gives"""
+    from common import vah_cells as ref_vah_cells
+    cols = synthetic.surface_vah(64, 1005)
+    mine = api.vah_cells(cols, fx)
+    with tempfile.TemporaryDirectory() as wd:
+        workdir.materialize(wd, surface_columns=cols, fixture=fx, hrg_eos=1, mode=2, vah=True)
+        d = host_dump(wd)
+    for k in ("aL", "Lambda", "c0", "c1", "c2", "c3", "c4"):
+        assert np.array_equal(mine[k], d[k]), k
+    ref = ref_vah_cells(cols, fx)
+    for k in ("aL", "Lambda", "c0", "c4"):
+        assert np.allclose(mine[k], ref[k], rtol=1e-12, atol=0), k
