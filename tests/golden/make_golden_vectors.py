@@ -36,6 +36,10 @@ CASES = {
     "s3stress_df2": ("vh", dict(three_d=True, stress=True), 100, 7, "chosen_pikp", dict(hrg_eos=1, dimension=3, df_mode=2), "kernel"),
     "s2_df1": ("vh", dict(three_d=False), 30, 1002, "chosen_pikp", dict(hrg_eos=1, dimension=2, df_mode=1), "full"),
     "s2_df3": ("vh", dict(three_d=False), 30, 1002, "chosen_pikp", dict(hrg_eos=1, dimension=2, df_mode=3), "kernel"),
+    "s2_df2": ("vh", dict(three_d=False), 30, 1002, "chosen_pikp", dict(hrg_eos=1, dimension=2, df_mode=2), "kernel"),
+    "s2_df4": ("vh", dict(three_d=False), 30, 1002, "chosen_pikp", dict(hrg_eos=1, dimension=2, df_mode=4), "kernel"),
+    "s2stress_df3": ("vh", dict(three_d=False, stress=True), 24, 8, "chosen_pikp", dict(hrg_eos=1, dimension=2, df_mode=3), "kernel"),
+    "s3stress_df4": ("vh", dict(three_d=True, stress=True), 100, 7, "chosen_pikp", dict(hrg_eos=2, dimension=3, df_mode=4), "kernel"),
     "s2_ideal": ("vh", dict(three_d=False, viscous=False), 30, 1002, "chosen_pikp",
                  dict(hrg_eos=1, dimension=2, df_mode=1, include_bulk_deltaf=0, include_shear_deltaf=0), "kernel"),
     "s3_heavy_df1": ("vh", dict(three_d=True), 60, 1003, HEAVY, dict(hrg_eos=1, dimension=3, df_mode=1), "kernel"),
