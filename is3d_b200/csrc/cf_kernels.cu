@@ -202,9 +202,10 @@ cf_kernel(const HotParams hp)
         const double2 *pr = reinterpret_cast<const double2 *>(Ps + (c * NPT + k) * kRec);
         const double2 v0 = pr[0], v1 = pr[1], v2 = pr[2];
         if (MODEL == M_FEQMOD) {
-          const double tp2 = pT + pT;
-          g1[k] = tp2 * v0.x; g2[k] = tp2 * v0.y; g3[k] = tp2 * v1.x;      // 2 pT w
-          g0[k] = fma(pT2, v1.y, K0m);                                     // pT^2 |w|^2 + (m/T_mod)^2
+          // p'/T_mod = mT v + pT w is formed component-wise and then squared: expanding |p'|^2 into |v|^2, v.w, |w|^2 would
+          // amplify rounding by the square of A^-1's largest eigenvalue (cells with detA << 1)
+          g1[k] = pT * v0.x; g2[k] = pT * v0.y; g3[k] = pT * v1.x;         // pT w
+          g0[k] = K0m;                                                     // (m/T_mod)^2
           pd[k] = pT * v2.x; q[k] = 0.0;
         } else {
           q[k] = pT * v0.x;                 // pT * (cos ux + sin uy)/T
@@ -220,12 +221,12 @@ cf_kernel(const HotParams hp)
         const double2 *yr = reinterpret_cast<const double2 *>(Ys + (c * nst + j) * RY);
         const double2 v0 = yr[0], v1 = yr[1], v2 = yr[2];
         if (MODEL == M_FEQMOD) {
-          const double e1 = mT * v0.x, e2 = mT * v0.y, e3 = mT * v1.x, h0 = mT2 * v1.y, cpm = mT * v2.x, w = v2.y;
+          const double e1 = mT * v0.x, e2 = mT * v0.y, e3 = mT * v1.x, cpm = mT * v2.x, w = v2.y;
           if (SB == 0) {
 #pragma unroll
             for (int k = 0; k < NPT; k++) {
-              double E2 = h0 + g0[k];
-              E2 = fma(e1, g1[k], E2); E2 = fma(e2, g2[k], E2); E2 = fma(e3, g3[k], E2);   // (E'/T_mod)^2
+              const double p1 = e1 + g1[k], p2 = e2 + g2[k], p3 = e3 + g3[k];
+              double E2 = fma(p1, p1, g0[k]); E2 = fma(p2, p2, E2); E2 = fma(p3, p3, E2);   // (E'/T_mod)^2
               const double x = sqrt_fast(E2);
               const double pds = fma(w, pd[k], cpm);
               if (exp_finite(x)) {
@@ -237,8 +238,8 @@ cf_kernel(const HotParams hp)
             double xv[NPT], pv[NPT], av[NPT]; bool lv[NPT]; bool any = false;
 #pragma unroll
             for (int k = 0; k < NPT; k++) {
-              double E2 = h0 + g0[k];
-              E2 = fma(e1, g1[k], E2); E2 = fma(e2, g2[k], E2); E2 = fma(e3, g3[k], E2);
+              const double p1 = e1 + g1[k], p2 = e2 + g2[k], p3 = e3 + g3[k];
+              double E2 = fma(p1, p1, g0[k]); E2 = fma(p2, p2, E2); E2 = fma(p3, p3, E2);
               xv[k] = sqrt_fast(E2);
               lv[k] = exp_finite(xv[k]);
               any |= lv[k];

@@ -224,13 +224,26 @@ __device__ void lu_inverse3(const double Ain[9], double inv[9])
   }
 }
 
+// v = A^-1 b with iterative refinement (the reference refines p' = A^-1 p per momentum, smooth_kernels.cpp:907-919; applying
+// the same sweeps to the factor vectors is equivalent by linearity and keeps ill-conditioned cells, detA << 1, in parity)
+__device__ __forceinline__ void solve_refined3(const double A[9], const double Ainv[9], const double b[3], double v[3])
+{
+  for (int i = 0; i < 3; i++) v[i] = Ainv[i * 3 + 0] * b[0] + Ainv[i * 3 + 1] * b[1] + Ainv[i * 3 + 2] * b[2];
+  for (int it = 0; it < 5; it++) {
+    double r[3];
+    for (int i = 0; i < 3; i++) r[i] = __fma_rn(-A[i * 3 + 2], v[2], __fma_rn(-A[i * 3 + 1], v[1], __fma_rn(-A[i * 3 + 0], v[0], b[i])));
+    if (r[0] == 0.0 && r[1] == 0.0 && r[2] == 0.0) break;
+    for (int i = 0; i < 3; i++) v[i] += Ainv[i * 3 + 0] * r[0] + Ainv[i * 3 + 1] * r[1] + Ainv[i * 3 + 2] * r[2];
+  }
+}
+
 struct CellFM {
   // common
   double tau, eta, inv_tau, ut, ux, uy, un, dat, dax, day, dan;
   // linear (breakdown / narrow) branch: Chapman-Enskog or Jonah-linear coefficients, x = u.p / T
   double invT, scl, pitt, pitx, pity, pitn, pixx, pixy, pixn, piyy, piyn, pinn;
   // feqmod branch
-  double Xt, Xx, Xy, Xn, Yx, Yy, Zt, Zn, Ainv[9], invTmod, detA, eta_scale;
+  double Xt, Xx, Xy, Xn, Yx, Yy, Zt, Zn, A[9], Ainv[9], invTmod, detA, eta_scale;
   int valid, breaks_down;
 };
 
@@ -316,6 +329,7 @@ prepare_feqmod_kernel(RawCells cells, PrepTables tab, Layout L, int include_shea
         const double Ayy = 1.0 + piyy_LRF * shear_mod + bulk_mod, Ayz = piyz_LRF * shear_mod, Azz = 1.0 + pizz_LRF * shear_mod + bulk_mod;
         const double detA = Axx * (Ayy * Azz - Ayz * Ayz) - Axy * (Axy * Azz - Ayz * Axz) + Axz * (Axy * Ayz - Ayy * Axz);
         const double A[9] = {Axx, Axy, Axz, Axy, Ayy, Ayz, Axz, Ayz, Azz};
+        for (int q9 = 0; q9 < 9; q9++) c.A[q9] = A[q9];
         lu_inverse3(A, c.Ainv);
         const double neq_fact = T * T * T / two_pi2_hbarC3, J20_fact = T * neq_fact;
         int breaks = 0;
@@ -400,10 +414,10 @@ prepare_feqmod_kernel(RawCells cells, PrepTables tab, Layout L, int include_shea
       const double arg = yv - c.eta_scale * eta;
       const double ch = cosh(arg), sh = sinh(arg), tsh = c.tau * sh;
       // p_LRF = mT V + pT W with V = (-Xt ch + Xn tau sh, 0, -Zt ch + Zn tau sh)   (:889-891)
-      const double V0 = -c.Xt * ch + c.Xn * tsh, V2 = -c.Zt * ch + c.Zn * tsh;
-      const double v0 = (c.Ainv[0] * V0 + c.Ainv[2] * V2) * c.invTmod;
-      const double v1 = (c.Ainv[3] * V0 + c.Ainv[5] * V2) * c.invTmod;
-      const double v2 = (c.Ainv[6] * V0 + c.Ainv[8] * V2) * c.invTmod;
+      const double Vv[3] = {-c.Xt * ch + c.Xn * tsh, 0.0, -c.Zt * ch + c.Zn * tsh};
+      double sol[3];
+      solve_refined3(c.A, c.Ainv, Vv, sol);
+      const double v0 = sol[0] * c.invTmod, v1 = sol[1] * c.invTmod, v2 = sol[2] * c.invTmod;
       rf[0] = v0; rf[1] = v1; rf[2] = v2; rf[3] = v0 * v0 + v1 * v1 + v2 * v2;
       rf[4] = wgt * (ch * c.dat) + (sh * c.inv_tau) * c.dan;                   // :884
       rf[5] = wgt;
@@ -430,10 +444,10 @@ prepare_feqmod_kernel(RawCells cells, PrepTables tab, Layout L, int include_shea
     rl[3] = 2.0 * c.scl * (c.pitx * cs + c.pity * sn);
     rl[4] = 2.0 * c.scl * (c.pixn * cs + c.piyn * sn);
     if (!c.breaks_down) {
-      const double W0 = c.Xx * cs + c.Xy * sn, W1 = c.Yx * cs + c.Yy * sn;
-      const double w0 = (c.Ainv[0] * W0 + c.Ainv[1] * W1) * c.invTmod;
-      const double w1 = (c.Ainv[3] * W0 + c.Ainv[4] * W1) * c.invTmod;
-      const double w2 = (c.Ainv[6] * W0 + c.Ainv[7] * W1) * c.invTmod;
+      const double Wv[3] = {c.Xx * cs + c.Xy * sn, c.Yx * cs + c.Yy * sn, 0.0};
+      double sol[3];
+      solve_refined3(c.A, c.Ainv, Wv, sol);
+      const double w0 = sol[0] * c.invTmod, w1 = sol[1] * c.invTmod, w2 = sol[2] * c.invTmod;
       rf[0] = w0; rf[1] = w1; rf[2] = w2; rf[3] = w0 * w0 + w1 * w1 + w2 * w2;
       rf[4] = cs * c.dax + sn * c.day;
     }
