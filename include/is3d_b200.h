@@ -111,6 +111,28 @@ int is3d_b200_smooth_spectra(const is3d_flags *flags, const is3d_surface *surfac
                              const is3d_grid *grid, const is3d_df_tables *df, const is3d_laguerre *laguerre,
                              const is3d_options *options, double *dN_out, is3d_stats *stats);
 
+/* ---- operation = 0: spacetime distributions of the momentum-integrated yield -------------------
+ * Replaces EmissionFunctionArray::calculate_dN_dX (emissionfunction_smooth_kernels.cpp:1000-1446, df_mode 1, 2) and
+ * calculate_dN_dX_feqmod (:1449-2135, df_mode 3, 4), called from calculate_spectra (emissionfunction.cpp:1514, 1579).
+ * Every cell's yield  sum_{pT, phi, y} w_pT w_phi g/(2 pi hbar c)^3 sum_eta p.dsigma f  (3+1D: all y points, unweighted,
+ * like the reference) is binned by the cell's tau and r = sqrt(x^2 + y^2):
+ *    itau = floor((tau - tau_min) / ((tau_max - tau_min) / tau_bins)),  ir likewise (:1376-1400).
+ * Results are the RAW sums the reference accumulates; its writers divide by the bin volumes (:1404-1435), see
+ * is3d_b200_write_spacetime().  Arrays are caller-allocated host memory and are OVERWRITTEN:
+ *    dN_tau [n_species][tau_bins]   dN_r [n_species][r_bins]   dN_taur [n_species][tau_bins][r_bins]
+ *    dN_dydeta [n_species][eta_pts] (eta_pts = 1 in 3+1D, n_eta in 2+1D)   dN_dy [n_species]                      */
+typedef struct {
+  double tau_min, tau_max, r_min, r_max;   /* iS3D_parameters.dat: tau_min, tau_max, r_min, r_max */
+  int32_t tau_bins, r_bins;                /* tau_bins, r_bins */
+  const double *x, *y;                     /* [n_cells] transverse cell positions, same memory space as the surface arrays */
+  const double *pT_weight, *phi_weight;    /* host: second column of the pT and phi tables */
+} is3d_spacetime_bins;
+typedef struct { double *dN_tau, *dN_r, *dN_taur, *dN_dydeta, *dN_dy; } is3d_spacetime_result;
+int is3d_b200_spacetime_distributions(const is3d_flags *flags, const is3d_surface *surface, const is3d_species *species,
+                                      const is3d_grid *grid, const is3d_df_tables *df, const is3d_laguerre *laguerre,
+                                      const is3d_spacetime_bins *bins, const is3d_options *options,
+                                      is3d_spacetime_result *result, is3d_stats *stats);
+
 /* FP64 FMA peak of the current device measured with a dependency-free DFMA chain (the roofline denominator;
  * MEASURED_PEAKS.json carries no FP64 figure).  Returns TFLOP/s in *tflops, SM clock not touched. */
 int is3d_b200_measure_fp64_peak(double *tflops, double *ms);

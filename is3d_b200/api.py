@@ -210,16 +210,7 @@ def make_flags(flags, mode=1):
     return f
 
 
-def smooth_spectra(flags, cells, species, grid, df_tables=None, laguerre=None, out=None, memory="host",
-                   stream=None, n_chunks=0, tile_variant=0):
-    """Call is3d_b200_smooth_spectra.
-
-    cells: dict of per-cell arrays (numpy for memory='host', float64 CUDA tensors for memory='device').
-    Returns (dN, stats dict); dN is flat [y][phi][pT][species] (species fastest), numpy or the CUDA tensor `out`.
-    The result is ADDED into `out` when given.
-    """
-    device = (memory == "device")
-    m = _Marshal(device)
+def _marshal_problem(m, cells, species, grid, df_tables, laguerre):
     sf = Surface()
     n = len(cells["tau"]) if not _is_torch(cells["tau"]) else int(cells["tau"].numel())
     sf.n_cells = n
@@ -248,6 +239,20 @@ def smooth_spectra(flags, cells, species, grid, df_tables=None, laguerre=None, o
         la.n_points = len(laguerre["root1"])
         for k in ("root1", "weight1", "root2", "weight2"):
             setattr(la, k, m.host(laguerre[k]))
+    return sf, sp, g, dft, la
+
+
+def smooth_spectra(flags, cells, species, grid, df_tables=None, laguerre=None, out=None, memory="host",
+                   stream=None, n_chunks=0, tile_variant=0):
+    """Call is3d_b200_smooth_spectra.
+
+    cells: dict of per-cell arrays (numpy for memory='host', float64 CUDA tensors for memory='device').
+    Returns (dN, stats dict); dN is flat [y][phi][pT][species] (species fastest), numpy or the CUDA tensor `out`.
+    The result is ADDED into `out` when given.
+    """
+    device = (memory == "device")
+    m = _Marshal(device)
+    sf, sp, g, dft, la = _marshal_problem(m, cells, species, grid, df_tables, laguerre)
     n_bins = sp.n * g.n_pT * g.n_phi * g.n_y
     if device:
         import torch
@@ -268,4 +273,50 @@ def smooth_spectra(flags, cells, species, grid, df_tables=None, laguerre=None, o
     rc = lib().is3d_b200_smooth_spectra(C.byref(fl), C.byref(sf), C.byref(sp), C.byref(g), C.byref(dft), C.byref(la),
                                         C.byref(opt), out_ptr, C.byref(st))
     _check(rc)
+    return out, st.as_dict()
+
+
+class SpacetimeBins(C.Structure):
+    _fields_ = [("tau_min", C.c_double), ("tau_max", C.c_double), ("r_min", C.c_double), ("r_max", C.c_double),
+                ("tau_bins", C.c_int32), ("r_bins", C.c_int32), ("x", _D), ("y", _D), ("pT_weight", _D), ("phi_weight", _D)]
+
+
+class SpacetimeResult(C.Structure):
+    _fields_ = [(k, _D) for k in ("dN_tau", "dN_r", "dN_taur", "dN_dydeta", "dN_dy")]
+
+
+def spacetime_distributions(flags, cells, species, grid, df_tables, laguerre, bins, memory="host", stream=None,
+                            n_chunks=0, tile_variant=0):
+    """Call is3d_b200_spacetime_distributions (operation = 0).
+
+    cells must also carry the transverse positions "x", "y"; grid the quadrature weights "pT_weight", "phi_weight";
+    bins = dict(tau_min, tau_max, tau_bins, r_min, r_max, r_bins).  Returns (dict of raw sums as numpy arrays:
+    dN_tau [species][tau], dN_r [species][r], dN_taur [species][tau][r], dN_dydeta [species][eta_pts], dN_dy [species]; stats)."""
+    device = (memory == "device")
+    m = _Marshal(device)
+    sf, sp, g, dft, la = _marshal_problem(m, cells, species, grid, df_tables, laguerre)
+    b = SpacetimeBins()
+    b.tau_min, b.tau_max, b.r_min, b.r_max = (float(bins[k]) for k in ("tau_min", "tau_max", "r_min", "r_max"))
+    b.tau_bins, b.r_bins = int(bins["tau_bins"]), int(bins["r_bins"])
+    b.x = m.cells(cells["x"]); b.y = m.cells(cells["y"])
+    b.pT_weight = m.host(grid["pT_weight"]); b.phi_weight = m.host(grid["phi_weight"])
+    ns = sp.n; eta_pts = g.n_eta if flags["dimension"] == 2 else 1
+    out = dict(dN_tau=np.zeros((ns, b.tau_bins)), dN_r=np.zeros((ns, b.r_bins)), dN_taur=np.zeros((ns, b.tau_bins, b.r_bins)),
+               dN_dydeta=np.zeros((ns, eta_pts)), dN_dy=np.zeros(ns))
+    res = SpacetimeResult()
+    for k in out:
+        setattr(res, k, out[k].ctypes.data_as(_D))
+    if device and stream is None:
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+    opt = Options(); opt.memory = 1 if device else 0
+    opt.stream = C.c_void_p(stream or 0); opt.n_chunks = n_chunks; opt.tile_variant = tile_variant
+    st = Stats()
+    fl = make_flags(flags)
+    f = lib().is3d_b200_spacetime_distributions
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(Flags), C.POINTER(Surface), C.POINTER(Species), C.POINTER(Grid), C.POINTER(DfTables),
+                  C.POINTER(Laguerre), C.POINTER(SpacetimeBins), C.POINTER(Options), C.POINTER(SpacetimeResult), C.POINTER(Stats)]
+    _check(f(C.byref(fl), C.byref(sf), C.byref(sp), C.byref(g), C.byref(dft), C.byref(la), C.byref(b), C.byref(opt),
+             C.byref(res), C.byref(st)))
     return out, st.as_dict()

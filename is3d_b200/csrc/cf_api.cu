@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -44,14 +45,14 @@ struct DevBuf {
 };
 
 struct Workspace {
-  DevBuf raw, small, Y, P, S, Y2, P2, S2, partial, dN, counters, extra;
+  DevBuf raw, small, Y, P, S, Y2, P2, S2, partial, dN, counters, extra, gather, integ, integ_out;
   cudaEvent_t ev[8];
   bool events = false;
   void release()
   {
     raw.release(); small.release(); Y.release(); P.release(); S.release(); Y2.release(); P2.release(); S2.release();
     partial.release(); dN.release();
-    counters.release(); extra.release();
+    counters.release(); extra.release(); gather.release(); integ.release(); integ_out.release();
     if (events) { for (auto &e : ev) cudaEventDestroy(e); events = false; }
   }
 };
@@ -70,6 +71,21 @@ struct SmallArena {
 };
 
 static int fail(int code, const char *msg) { g_last_error = msg; return code; }
+
+// operation = 0: what the core returns instead of spectra bins (see HotParams::integ_mode)
+struct IntegRequest {
+  int mode = 1;                               // 1: per (tau, r) category of cells;  2: per eta slot (2+1D rapidity distribution)
+  const double *pT_weight = nullptr, *phi_weight = nullptr;    // host
+  const int32_t *category = nullptr;          // mode 1, host: category of every cell, 0 <= category < n_categories
+  int n_categories = 0;
+  std::vector<int32_t> unit_category;         // out, mode 1: category of every unit (= cell chunk)
+  std::vector<double> result;                 // out: [n_units][n_species]
+  int n_units = 0;
+};
+
+static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_species *sp, const is3d_grid *gr,
+                       const is3d_df_tables *df, const is3d_laguerre *gla, const is3d_options *opt_in,
+                       double *dN_out, is3d_stats *stats, IntegRequest *iq);
 
 }  // namespace is3d
 
@@ -170,7 +186,19 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
                              const is3d_df_tables *df, const is3d_laguerre *gla, const is3d_options *opt_in,
                              double *dN_out, is3d_stats *stats)
 {
-  if (!fl || !sf || !sp || !gr || !dN_out) return fail(IS3D_ERR_ARGUMENT, "NULL argument");
+  if (!dN_out) return fail(IS3D_ERR_ARGUMENT, "NULL argument");
+  return smooth_core(fl, sf, sp, gr, df, gla, opt_in, dN_out, stats, nullptr);
+}
+
+}  // extern "C"
+
+namespace is3d {
+
+static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_species *sp, const is3d_grid *gr,
+                       const is3d_df_tables *df, const is3d_laguerre *gla, const is3d_options *opt_in,
+                       double *dN_out, is3d_stats *stats, IntegRequest *iq)
+{
+  if (!fl || !sf || !sp || !gr || (!dN_out && !iq)) return fail(IS3D_ERR_ARGUMENT, "NULL argument");
   if (!g_init) { int rc = is3d_b200_init(); if (rc) return rc; }
   std::lock_guard<std::mutex> lk(g_mutex);
   is3d_options opt; memset(&opt, 0, sizeof(opt));
@@ -208,21 +236,42 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
   Layout L; memset(&L, 0, sizeof(L));
   L.n_species = sp->n; L.n_pT = gr->n_pT; L.n_phi = gr->n_phi; L.n_y_out = gr->n_y;
   L.dim2 = dim2 ? 1 : 0;
+  L.per_slot = (iq && iq->mode == 2) ? 1 : 0;
   L.n_slots = dim2 ? gr->n_eta : gr->n_y;
   L.rec_y = vah ? kRecVah : kRec;
+  const bool sum_slots = dim2 && !L.per_slot;               // the hot kernel folds the eta slots into one accumulator
+  if (iq && vah) return fail(IS3D_ERR_UNSUPPORTED, "spacetime distributions exist for mode 1 surfaces only");
+  if (iq && iq->mode == 2 && !dim2) return fail(IS3D_ERR_ARGUMENT, "per-slot integration is a 2+1D pass");
+  if (iq && (!iq->pT_weight || !iq->phi_weight)) return fail(IS3D_ERR_ARGUMENT, "pT / phi quadrature weights missing");
   // tile_variant: 0 = model default (tuned on B200, see profiles/), k > 0 = table entry k - 1 (tuning / tests)
   int variant;
   if (opt.tile_variant >= 1 && opt.tile_variant <= 16) variant = opt.tile_variant - 1;
-  else if (dim2_early) variant = (model == M_FEQMOD || model == M_VAH) ? 12 : (model == M_IDEAL ? 13 : 10);
+  else if (sum_slots) variant = (model == M_FEQMOD || model == M_VAH) ? 12 : (model == M_IDEAL ? 13 : 10);
   else variant = (model == M_FEQMOD || model == M_VAH) ? 12 : 9;
+  (void)dim2_early;
   int nyt, npt, ct;
-  hot_variant_shape(variant, L.dim2, &nyt, &npt, &ct);
-  L.nst = dim2 ? L.n_slots : nyt;
-  L.n_ytiles = dim2 ? 1 : (L.n_slots + nyt - 1) / nyt;
+  hot_variant_shape(variant, sum_slots ? 1 : 0, &nyt, &npt, &ct);
+  L.nst = sum_slots ? L.n_slots : nyt;
+  L.n_ytiles = sum_slots ? 1 : (L.n_slots + nyt - 1) / nyt;
   L.npt = npt; L.n_ptiles = (L.n_phi + npt - 1) / npt;
   L.ct = ct;
   L.n_cells = n_cells;
-  L.n_tiles = (n_cells + ct - 1) / ct;
+  // cells grouped by category ((tau, r) bin): every category starts on a tile boundary
+  std::vector<int64_t> cat_tiles;                           // tiles per category
+  if (iq && iq->mode == 1) {
+    if ((!iq->category && n_cells > 0) || iq->n_categories <= 0) return fail(IS3D_ERR_ARGUMENT, "cell categories missing");
+    std::vector<int64_t> count((size_t)iq->n_categories, 0);
+    for (int64_t i = 0; i < n_cells; i++) {
+      const int32_t c = iq->category[i];
+      if (c < 0 || c >= iq->n_categories) return fail(IS3D_ERR_ARGUMENT, "cell category out of range");
+      count[(size_t)c]++;
+    }
+    cat_tiles.resize(count.size());
+    L.n_tiles = 0;
+    for (size_t c = 0; c < count.size(); c++) { cat_tiles[c] = (count[c] + ct - 1) / ct; L.n_tiles += cat_tiles[c]; }
+  } else {
+    L.n_tiles = (n_cells + ct - 1) / ct;
+  }
   L.n_cells_pad = L.n_tiles * ct;
 
   const int n_pairs = sp->n * gr->n_pT;
@@ -250,7 +299,36 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
   }
   if ((int64_t)n_chunks > L.n_tiles) n_chunks = (int)(L.n_tiles > 0 ? L.n_tiles : 1);
   if (n_chunks < 1) n_chunks = 1;
-  if (n_bintiles * n_chunks > 2147483647LL) return fail(IS3D_ERR_ARGUMENT, "grid too large");
+  // operation = 0, mode 1: a chunk never crosses a category; large categories are split into chunks of ~ n_tiles / n_chunks tiles
+  std::vector<int64_t> gather_h, chunk_tiles_h;
+  const int integ_sl = (n_warps * 32 - 1) / gr->n_pT + 2;
+  if (iq && iq->mode == 1) {
+    const int64_t per_chunk = std::max<int64_t>(1, (L.n_tiles + n_chunks - 1) / n_chunks);
+    std::vector<int64_t> cat_first(cat_tiles.size() + 1, 0);              // first record position of every category
+    for (size_t c = 0; c < cat_tiles.size(); c++) cat_first[c + 1] = cat_first[c] + cat_tiles[c] * ct;
+    gather_h.assign((size_t)L.n_cells_pad, -1);
+    {
+      std::vector<int64_t> fill(cat_first.begin(), cat_first.end() - 1);
+      for (int64_t i = 0; i < n_cells; i++) gather_h[(size_t)fill[(size_t)iq->category[i]]++] = i;     // stable: cell order kept inside a category
+    }
+    iq->unit_category.clear();
+    chunk_tiles_h.push_back(0);
+    for (size_t c = 0; c < cat_tiles.size(); c++) {
+      const int64_t t0 = cat_first[c] / ct;
+      for (int64_t t = 0; t < cat_tiles[c]; t += per_chunk) {
+        chunk_tiles_h.push_back(t0 + std::min(cat_tiles[c], t + per_chunk));
+        iq->unit_category.push_back((int32_t)c);
+      }
+    }
+    n_chunks = (int)iq->unit_category.size();
+    iq->n_units = n_chunks;
+  } else if (iq) {
+    iq->n_units = L.n_ytiles * L.nst;
+  }
+  if (n_bintiles * (int64_t)n_chunks > 2147483647LL) return fail(IS3D_ERR_ARGUMENT, "grid too large");
+  const int64_t integ_rows = iq ? (int64_t)n_chunks * L.n_ytiles * (iq->mode == 2 ? L.nst : 1) : 0;
+  const size_t integ_bytes = (size_t)integ_rows * L.n_ptiles * n_groupblocks * integ_sl * 8;
+  if (iq && integ_bytes > ((size_t)8 << 30)) return fail(IS3D_ERR_ARGUMENT, "too many (tau, r) bins for the integration workspace");
 
   // ---- small tables -> one staging buffer
   SmallArena ar;
@@ -315,12 +393,17 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
     CU_CHECK(g_ws.S2.reserve(rec_S + 256));
     if (fl->df_mode == 3) CU_CHECK(g_ws.extra.reserve(((size_t)L.n_species + 8) * L.n_cells_pad * 8 + 256));
   }
-  CU_CHECK(g_ws.partial.reserve((size_t)partial_sets * n_chunks * n_bins * 8 + 256));
+  if (!iq) CU_CHECK(g_ws.partial.reserve((size_t)partial_sets * n_chunks * n_bins * 8 + 256));
+  if (iq) {
+    CU_CHECK(g_ws.integ.reserve((size_t)partial_sets * integ_bytes + 256));
+    CU_CHECK(g_ws.integ_out.reserve((size_t)partial_sets * iq->n_units * sp->n * 8 + 256));
+    CU_CHECK(g_ws.gather.reserve((gather_h.size() + chunk_tiles_h.size() + (size_t)gr->n_pT + gr->n_phi) * 8 + 1024));
+  }
   CU_CHECK(g_ws.counters.reserve(256));
   const size_t cell_stride = ((size_t)n_cells * 8 + 255) & ~(size_t)255;
   if (opt.memory == 0) {
     CU_CHECK(g_ws.raw.reserve(cell_stride * n_raw + 256));
-    CU_CHECK(g_ws.dN.reserve((size_t)n_bins * 8 + 256));
+    if (!iq) CU_CHECK(g_ws.dN.reserve((size_t)n_bins * 8 + 256));
   }
 
   cudaEvent_t *ev = g_ws.ev;
@@ -337,8 +420,28 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
       *items[a].dst = dst;
     } else *items[a].dst = items[a].src;
   }
-  double *dN_dev = (opt.memory == 0) ? g_ws.dN.as<double>() : dN_out;
-  if (opt.memory == 0) CU_CHECK(cudaMemsetAsync(dN_dev, 0, (size_t)n_bins * 8, st));
+  const int64_t *gather_d = nullptr, *chunk_tiles_d = nullptr;
+  const double *wpT_d = nullptr, *wphi_d = nullptr;
+  if (iq) {
+    unsigned char *g = g_ws.gather.as<unsigned char>();
+    size_t off = 0;
+    auto up = [&](const void *src, size_t bytes) -> const void * {
+      const void *d = g + off;
+      if (bytes) cudaMemcpyAsync(g + off, src, bytes, cudaMemcpyHostToDevice, st);
+      off = (off + bytes + 255) & ~(size_t)255;
+      return d;
+    };
+    if (iq->mode == 1) {
+      gather_d = (const int64_t *)up(gather_h.data(), gather_h.size() * 8);
+      chunk_tiles_d = (const int64_t *)up(chunk_tiles_h.data(), chunk_tiles_h.size() * 8);
+    }
+    wpT_d = (const double *)up(iq->pT_weight, (size_t)gr->n_pT * 8);
+    wphi_d = (const double *)up(iq->phi_weight, (size_t)gr->n_phi * 8);
+    CU_CHECK(cudaGetLastError());
+    rc.gather = gather_d;
+  }
+  double *dN_dev = iq ? nullptr : (opt.memory == 0) ? g_ws.dN.as<double>() : dN_out;
+  if (!iq && opt.memory == 0) CU_CHECK(cudaMemsetAsync(dN_dev, 0, (size_t)n_bins * 8, st));
   CU_CHECK(cudaMemsetAsync(g_ws.counters.p, 0, sizeof(PrepCounters), st));
   CU_CHECK(cudaEventRecord(ev[1], st));
 
@@ -380,6 +483,10 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
   const double hbarC = 0.197327053;
   hp.prefactor = vah ? 1.0 / (8.0 * (M_PI * M_PI * M_PI)) / hbarC / hbarC / hbarC      // smooth_kernels.cpp:2146
                      : pow(2.0 * M_PI * hbarC, -3);                                      // :36, :400
+  if (iq) {
+    hp.integ_mode = iq->mode; hp.integ_sl = integ_sl; hp.chunk_tiles = chunk_tiles_d;
+    hp.pT_weight = wpT_d; hp.phi_weight = wphi_d; hp.integ = g_ws.integ.as<double>();
+  }
   CU_CHECK(launch_hot(model, hp, variant, st, nullptr));
   stt.gpu_launches++;
   int reduce_sets = 1;
@@ -392,6 +499,7 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
       HotParams hl = hp;
       hl.Y = g_ws.Y2.as<double>(); hl.P = g_ws.P2.as<double>(); hl.S = g_ws.S2.as<double>();
       hl.partial = hp.partial + (size_t)n_chunks * n_bins; hl.renorm = nullptr;
+      if (iq) hl.integ = hp.integ + integ_bytes / 8;
       CU_CHECK(launch_hot(fl->df_mode == 3 ? M_LINCE : M_JONAHLIN, hl, variant, st, nullptr));
       stt.gpu_launches++;
       reduce_sets = 2;
@@ -400,20 +508,37 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
   CU_CHECK(cudaEventRecord(ev[3], st));
 
   // ---- reduce chunks, add into the result
-  CU_CHECK(launch_reduce(hp.partial, n_chunks * reduce_sets, n_bins, dim2 ? n_bins / gr->n_y : n_bins, dN_dev, st));
-  stt.gpu_launches++;
+  const size_t unit_vals = iq ? (size_t)iq->n_units * sp->n : 0;
+  if (iq) {
+    CU_CHECK(launch_integ_reduce(hp, iq->n_units, g_ws.integ_out.as<double>(), st));
+    stt.gpu_launches++;
+    if (reduce_sets == 2) {
+      HotParams hl = hp; hl.integ = hp.integ + integ_bytes / 8;
+      CU_CHECK(launch_integ_reduce(hl, iq->n_units, g_ws.integ_out.as<double>() + unit_vals, st));
+      stt.gpu_launches++;
+    }
+  } else {
+    CU_CHECK(launch_reduce(hp.partial, n_chunks * reduce_sets, n_bins, dim2 ? n_bins / gr->n_y : n_bins, dN_dev, st));
+    stt.gpu_launches++;
+  }
   CU_CHECK(cudaEventRecord(ev[4], st));
 
   // ---- device -> host
   std::vector<double> host_dN;
-  if (opt.memory == 0) {
+  if (iq) {
+    iq->result.assign(unit_vals * reduce_sets, 0.0);
+    if (unit_vals) CU_CHECK(cudaMemcpyAsync(iq->result.data(), g_ws.integ_out.p, unit_vals * reduce_sets * 8, cudaMemcpyDeviceToHost, st));
+  } else if (opt.memory == 0) {
     host_dN.resize((size_t)n_bins);
     CU_CHECK(cudaMemcpyAsync(host_dN.data(), dN_dev, (size_t)n_bins * 8, cudaMemcpyDeviceToHost, st));
   }
   CU_CHECK(cudaMemcpyAsync(&cnt, cnt_d, sizeof(cnt), cudaMemcpyDeviceToHost, st));
   CU_CHECK(cudaEventRecord(ev[5], st));
   CU_CHECK(cudaEventSynchronize(ev[5]));
-  if (opt.memory == 0)
+  if (iq) {
+    if (reduce_sets == 2) for (size_t i = 0; i < unit_vals; i++) iq->result[i] += iq->result[unit_vals + i];
+    iq->result.resize(unit_vals);
+  } else if (opt.memory == 0)
     for (int64_t i = 0; i < n_bins; i++) dN_out[i] += host_dN[(size_t)i];
 
   float ms;
@@ -432,4 +557,92 @@ int is3d_b200_smooth_spectra(const is3d_flags *fl, const is3d_surface *sf, const
   return IS3D_OK;
 }
 
-}  // extern "C"
+}  // namespace is3d
+
+extern "C" int is3d_b200_spacetime_distributions(const is3d_flags *fl, const is3d_surface *sf, const is3d_species *sp,
+                                                 const is3d_grid *gr, const is3d_df_tables *df, const is3d_laguerre *gla,
+                                                 const is3d_spacetime_bins *bins, const is3d_options *opt_in,
+                                                 is3d_spacetime_result *res, is3d_stats *stats)
+{
+  if (!fl || !sf || !sp || !gr || !bins || !res) return fail(IS3D_ERR_ARGUMENT, "NULL argument");
+  if (!res->dN_tau || !res->dN_r || !res->dN_taur || !res->dN_dydeta || !res->dN_dy) return fail(IS3D_ERR_ARGUMENT, "NULL result array");
+  if (bins->tau_bins <= 0 || bins->r_bins <= 0 || !(bins->tau_max > bins->tau_min) || !(bins->r_max > bins->r_min))
+    return fail(IS3D_ERR_ARGUMENT, "empty tau or r binning");
+  if ((int64_t)(bins->tau_bins + 1) * (bins->r_bins + 1) > (1 << 24)) return fail(IS3D_ERR_ARGUMENT, "too many (tau, r) bins");
+  const int64_t n = sf->n_cells;
+  if (n < 0) return fail(IS3D_ERR_ARGUMENT, "negative cell count");
+  if (n > 0 && (!sf->tau || !bins->x || !bins->y)) return fail(IS3D_ERR_ARGUMENT, "tau, x, y arrays are required");
+  if (fl->mode == 2) return fail(IS3D_ERR_UNSUPPORTED, "spacetime distributions exist for mode 1 surfaces only");
+  const bool device_mem = opt_in && opt_in->memory == 1;
+  if (!g_init) { int rc = is3d_b200_init(); if (rc) return rc; }
+
+  // ---- (tau, r) category of every cell on the host (:1376-1379); index tau_bins / r_bins = outside the histogram
+  std::vector<double> hbuf;
+  const double *tau = sf->tau, *x = bins->x, *y = bins->y;
+  if (device_mem && n > 0) {
+    hbuf.resize((size_t)n * 3);
+    if (cudaMemcpy(hbuf.data(), sf->tau, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(hbuf.data() + n, bins->x, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(hbuf.data() + 2 * n, bins->y, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+      return fail(IS3D_ERR_CUDA, "device -> host copy of tau, x, y failed");
+    tau = hbuf.data(); x = tau + n; y = x + n;
+  }
+  const int nt = bins->tau_bins, nr = bins->r_bins;
+  const double tau_width = (bins->tau_max - bins->tau_min) / (double)nt, r_width = (bins->r_max - bins->r_min) / (double)nr;
+  auto bin_of = [](double v, int nb) { return (v >= 0.0 && v < (double)nb) ? (int)v : nb; };   // NaN, negative, beyond the range -> nb
+  std::vector<int32_t> cat((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    const double r = sqrt(x[i] * x[i] + y[i] * y[i]);
+    const int itau = bin_of(floor((tau[i] - bins->tau_min) / tau_width), nt), ir = bin_of(floor((r - bins->r_min) / r_width), nr);
+    cat[(size_t)i] = itau * (nr + 1) + ir;
+  }
+
+  const int ns = sp->n;
+  const bool dim2 = (fl->dimension == 2);
+  const int eta_pts = dim2 ? gr->n_eta : 1;
+  IntegRequest iq;
+  iq.mode = 1; iq.pT_weight = bins->pT_weight; iq.phi_weight = bins->phi_weight;
+  iq.category = cat.data(); iq.n_categories = (nt + 1) * (nr + 1);
+  is3d_stats st1; memset(&st1, 0, sizeof(st1));
+  int rc = smooth_core(fl, sf, sp, gr, df, gla, opt_in, nullptr, &st1, &iq);
+  if (rc) return rc;
+  std::fill(res->dN_tau, res->dN_tau + (size_t)ns * nt, 0.0);
+  std::fill(res->dN_r, res->dN_r + (size_t)ns * nr, 0.0);
+  std::fill(res->dN_taur, res->dN_taur + (size_t)ns * nt * nr, 0.0);
+  std::fill(res->dN_dydeta, res->dN_dydeta + (size_t)ns * eta_pts, 0.0);
+  std::fill(res->dN_dy, res->dN_dy + (size_t)ns, 0.0);
+  for (int u = 0; u < iq.n_units; u++) {                    // units come in (itau, ir) order: fixed summation order
+    const int itau = iq.unit_category[(size_t)u] / (nr + 1), ir = iq.unit_category[(size_t)u] % (nr + 1);
+    for (int s = 0; s < ns; s++) {
+      const double v = iq.result[(size_t)u * ns + s];
+      res->dN_dy[s] += v;
+      if (itau < nt) {
+        res->dN_tau[(size_t)s * nt + itau] += v;
+        if (ir < nr) res->dN_taur[((size_t)s * nt + itau) * nr + ir] += v;
+      }
+      if (ir < nr) res->dN_r[(size_t)s * nr + ir] += v;
+    }
+  }
+  if (!dim2) {
+    for (int s = 0; s < ns; s++) res->dN_dydeta[s] = res->dN_dy[s];          // eta_weight = 1: the same sum (:1352 vs :1357)
+  } else {
+    // rapidity distribution: a second pass that keeps the eta slots apart and integrates over (pT, phi) only
+    IntegRequest iq2;
+    iq2.mode = 2; iq2.pT_weight = bins->pT_weight; iq2.phi_weight = bins->phi_weight;
+    is3d_stats st2; memset(&st2, 0, sizeof(st2));
+    rc = smooth_core(fl, sf, sp, gr, df, gla, opt_in, nullptr, &st2, &iq2);
+    if (rc) return rc;
+    for (int j = 0; j < eta_pts; j++) {
+      const double w = gr->eta_weight[j];
+      for (int s = 0; s < ns; s++) {
+        const double v = iq2.result[(size_t)j * ns + s];
+        res->dN_dydeta[(size_t)s * eta_pts + j] = (v == 0.0 && w == 0.0) ? 0.0 : v / w;
+      }
+    }
+    st1.h2d_ms += st2.h2d_ms; st1.prepare_ms += st2.prepare_ms; st1.kernel_ms += st2.kernel_ms; st1.reduce_ms += st2.reduce_ms;
+    st1.d2h_ms += st2.d2h_ms; st1.total_ms += st2.total_ms; st1.gpu_launches += st2.gpu_launches; st1.evaluations += st2.evaluations;
+  }
+  if (stats) *stats = st1;
+  return IS3D_OK;
+}
+

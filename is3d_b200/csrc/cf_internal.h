@@ -15,6 +15,7 @@ constexpr int kStages = 4;       // TMA pipeline depth
 // Device-side view of the raw surface (GeV/fm units), NULL where switched off
 struct RawCells {
   int64_t n;
+  const int64_t *gather;      // NULL: record position = cell index; else source cell of every padded record position, -1 = padding
   const double *tau, *eta, *dat, *dax, *day, *dan, *ux, *uy, *un, *T, *P, *E;
   const double *pixx, *pixy, *pixn, *piyy, *piyn, *bulkPi;
   const double *pitt, *pitx, *pity, *pitn, *pinn, *Wx, *Wy, *Lambda, *aL, *c0, *c1, *c2, *c3, *c4;
@@ -40,7 +41,8 @@ struct PrepTables {
 struct Layout {
   int n_species, n_pT, n_phi, n_y_out;   // output array dims (n_y_out = y table length)
   int n_slots;                           // rapidity slots per cell: n_y (3+1D) or n_eta (2+1D)
-  int dim2;
+  int dim2;                              // dimension == 2: slots are the eta table (y = 0), else the y table at the cell's eta
+  int per_slot;                          // dim2 only: keep the eta slots apart (3+1D-shaped tiles) instead of summing them
   int nst, n_ytiles, npt, n_ptiles;
   int rec_y;                             // doubles per slot record (kRec or kRecVah)
   int ct;                                // cells per TMA tile
@@ -69,6 +71,12 @@ struct HotParams {
   long long outflow_thr;                           // bit pattern threshold of the p.dsigma > 0 test
   double prefactor;
   int regulate_thr;                                // high-word threshold of |df| >= 1, see clamp_unit()
+  // operation = 0 (spacetime distributions): momentum-integrated epilogue instead of the spectra bins
+  int integ_mode;                                  // 0 spectra; 1 sum over (slot, phi, pT) per chunk; 2 per slot, sum over (phi, pT)
+  int integ_sl;                                    // species slots per block: (block lanes - 1) / n_pT + 2
+  const int64_t *chunk_tiles;                      // [n_chunks + 1] first cell tile of every chunk (NULL: balanced split)
+  const double *pT_weight, *phi_weight;            // quadrature weights of the pT and phi tables
+  double *integ;                                   // mode 1: [chunk][ytile][ptile][groupblock][sl]; mode 2: [chunk][slot][ptile][groupblock][sl]
 };
 
 // launchers (cf_prepare.cu / cf_kernels.cu)
@@ -82,6 +90,8 @@ cudaError_t launch_prepare_vah(const is3d_flags &fl, const RawCells &cells, cons
                                double *Y, double *P, double *S, PrepCounters *counters, cudaStream_t st);
 cudaError_t launch_hot(int model, const HotParams &hp, int variant, cudaStream_t st, size_t *smem_out);
 cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, int64_t n_active, double *out, cudaStream_t st);
+// integ -> out[unit][species], unit = chunk (mode 1) or slot (mode 2, summed over chunks)
+cudaError_t launch_integ_reduce(const HotParams &hp, int n_units, double *out, cudaStream_t st);
 cudaError_t launch_fp64_peak(double *sink, int iters, cudaStream_t st, int *blocks, int *threads, long long *dfma_per_thread);
 void hot_variant_shape(int variant, int dim2, int *nyt, int *npt, int *ct);
 

@@ -144,9 +144,9 @@ cf_kernel(const HotParams hp)
   const long long thr = hp.outflow_thr;
   const double *renorm = (MODEL == M_FEQMOD && hp.renorm) ? hp.renorm + (int64_t)ipart * L.n_cells_pad : nullptr;
 
-  // ---- cell tiles of this chunk: balanced contiguous split of [0, n_tiles)
-  const int64_t t_begin = (L.n_tiles * (int64_t)chunk) / hp.n_chunks;
-  const int64_t t_end = (L.n_tiles * (int64_t)(chunk + 1)) / hp.n_chunks;
+  // ---- cell tiles of this chunk: balanced contiguous split of [0, n_tiles), or the caller's table ((tau, r) bins)
+  const int64_t t_begin = hp.chunk_tiles ? hp.chunk_tiles[chunk] : (L.n_tiles * (int64_t)chunk) / hp.n_chunks;
+  const int64_t t_end = hp.chunk_tiles ? hp.chunk_tiles[chunk + 1] : (L.n_tiles * (int64_t)(chunk + 1)) / hp.n_chunks;
   const int n_my_tiles = (int)(t_end - t_begin);
 
   const double *Yg = hp.Y + ((int64_t)ty * L.n_cells_pad) * nst * RY;
@@ -442,6 +442,45 @@ cf_kernel(const HotParams hp)
     if (threadIdx.x == 0 && t + kStages < n_my_tiles) issue(t + kStages);
   }
 
+  // ---- operation = 0 epilogue: integrate over (pT, phi) with the table weights (smooth_kernels.cpp:1284-1371), one
+  //      number per (species, chunk) -- or per (species, slot) -- instead of the spectra bins
+  if (hp.integ_mode) {
+    constexpr int NJ = DIM2 ? 1 : NYT;
+    const int per_slot = (hp.integ_mode == 2) ? NJ : 1;
+    double *red = stage_base;                           // [per_slot][blockDim.x]; every stage has been consumed
+    const double wl = lane_valid ? hp.pT_weight[ipT] * (hp.prefactor * hp.degeneracy[ipart]) : 0.0;
+    double tot = 0.0;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      double sj = 0.0;
+      const bool slot_ok = DIM2 || ty * NYT + j < L.n_slots;
+#pragma unroll
+      for (int k = 0; k < NPT; k++) {
+        const int iphi = tp * NPT + k;
+        if (slot_ok && iphi < L.n_phi) sj = fma(hp.phi_weight[iphi], acc[(DIM2 ? 0 : j * NPT) + k], sj);
+      }
+      if (hp.integ_mode == 2) red[j * blockDim.x + threadIdx.x] = wl * sj;
+      tot += sj;
+    }
+    if (hp.integ_mode == 1) red[threadIdx.x] = wl * tot;
+    __syncthreads();
+    const int pair0 = gb * (int)blockDim.x, n_pairs = L.n_species * L.n_pT;
+    const int s_first = pair0 / L.n_pT;
+    for (int w = threadIdx.x; w < per_slot * hp.integ_sl; w += blockDim.x) {
+      const int j = w / hp.integ_sl, sl = w - j * hp.integ_sl;
+      const int sidx = s_first + sl;
+      int lo = sidx * L.n_pT, hi = lo + L.n_pT;
+      if (lo < pair0) lo = pair0;
+      if (hi > pair0 + (int)blockDim.x) hi = pair0 + (int)blockDim.x;
+      if (hi > n_pairs) hi = n_pairs;
+      double v = 0.0;
+      for (int q = lo; q < hi; q++) v += red[j * blockDim.x + (q - pair0)];
+      const int64_t unit = (hp.integ_mode == 2) ? (int64_t)chunk * (L.n_ytiles * NJ) + ty * NJ + j : (int64_t)chunk * L.n_ytiles + ty;
+      hp.integ[((unit * L.n_ptiles + tp) * hp.n_groupblocks + gb) * hp.integ_sl + sl] = v;
+    }
+    return;
+  }
+
   // ---- epilogue: partial[chunk][ipart + n_species (ipT + n_pT (iphi + n_phi iy))]
   if (lane_valid) {
     const double scale = hp.prefactor * hp.degeneracy[ipart];
@@ -471,6 +510,40 @@ __global__ void reduce_kernel(const double *__restrict__ partial, int n_chunks, 
   double s = 0.0;
   for (int c = 0; c < n_chunks; c++) s += partial[(int64_t)c * n_bins + i];
   out[i] += s;
+}
+
+// integ -> out[unit][species]: fixed summation order (chunk, y tile, phi tile, group block), no atomics
+__global__ void integ_reduce_kernel(const HotParams hp, int n_units, int nj, int block_lanes, double *__restrict__ out)
+{
+  const Layout &L = hp.L;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n_units * L.n_species) return;
+  const int unit = (int)(i / L.n_species), sidx = (int)(i - (int64_t)unit * L.n_species);
+  const int gb_lo = (sidx * L.n_pT) / block_lanes, gb_hi = ((sidx + 1) * L.n_pT - 1) / block_lanes;
+  double v = 0.0;
+  auto add = [&](int64_t row) {                          // row = index of a [ptile][groupblock][sl] slab
+    for (int tp = 0; tp < L.n_ptiles; tp++)
+      for (int gb = gb_lo; gb <= gb_hi; gb++) {
+        const int sl = sidx - (gb * block_lanes) / L.n_pT;
+        v += hp.integ[((row * L.n_ptiles + tp) * hp.n_groupblocks + gb) * hp.integ_sl + sl];
+      }
+  };
+  if (hp.integ_mode == 1) {                              // unit = chunk: sum the y tiles
+    for (int ty = 0; ty < L.n_ytiles; ty++) add((int64_t)unit * L.n_ytiles + ty);
+  } else {                                               // unit = slot: sum the chunks
+    for (int c = 0; c < hp.n_chunks; c++) add((int64_t)c * (L.n_ytiles * nj) + unit);
+  }
+  out[i] = v;
+}
+
+cudaError_t launch_integ_reduce(const HotParams &hp, int n_units, double *out, cudaStream_t st)
+{
+  const int64_t n = (int64_t)n_units * hp.L.n_species;
+  if (n == 0) return cudaSuccess;
+  const bool summed = hp.L.dim2 && !hp.L.per_slot;
+  const int nj = summed ? 1 : hp.L.nst;
+  integ_reduce_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(hp, n_units, nj, hp.n_warps * 32, out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, int64_t n_active, double *out, cudaStream_t st)
@@ -522,7 +595,7 @@ template <int MODEL>
 static cudaError_t launch_model(const HotParams &hp, int variant, cudaStream_t st, size_t *smem_out)
 {
   constexpr bool TUNE = true;
-  if (hp.L.dim2) {
+  if (hp.L.dim2 && !hp.L.per_slot) {
     switch (variant) {
       case 1: return launch_one<MODEL, 1, 4, true, 4, 0>(hp, st, smem_out);
       case 2: return launch_one<MODEL, 1, 6, true, 3, 0>(hp, st, smem_out);

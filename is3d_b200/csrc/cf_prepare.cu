@@ -37,6 +37,14 @@ struct CellVH {
   int valid;
 };
 
+// record position -> cell of the caller's arrays (-1: padding).  Positions differ from cell indices when the cells have
+// been grouped by (tau, r) bin for the spacetime distributions.
+__device__ __forceinline__ int64_t source_cell(const RawCells &cells, const Layout &L, int64_t pos)
+{
+  if (cells.gather) return pos < L.n_cells_pad ? cells.gather[pos] : -1;
+  return pos < cells.n ? pos : -1;
+}
+
 constexpr int kPrepCells = 16;      // cells per prepare block
 constexpr int kPrepThreads = 128;
 
@@ -54,11 +62,11 @@ prepare_vh_kernel(RawCells cells, PrepTables tab, Layout L, int include_shear, i
 
   // ---- phase 1: one thread per cell, scalar set-up (smooth_kernels.cpp:118-242)
   if (threadIdx.x < kPrepCells) {
-    const int64_t i = cell0 + threadIdx.x;
+    const int64_t i = source_cell(cells, L, cell0 + threadIdx.x);
     CellVH c;
     c.valid = 0;
     double K0 = 0.0, K2 = 0.0;
-    if (i < cells.n) {
+    if (i >= 0) {
       const double tau = cells.tau[i], tau2 = tau * tau;
       const double ux = cells.ux[i], uy = cells.uy[i], un = cells.un[i];
       const double ut = sqrt(1.0 + ux * ux + uy * uy + tau2 * un * un);
@@ -260,12 +268,12 @@ prepare_feqmod_kernel(RawCells cells, PrepTables tab, Layout L, int include_shea
   const double two_pi2_hbarC3 = 2.0 * pow(M_PI, 2) * pow(0.197327053, 3);
 
   if (threadIdx.x < kPrepCells) {
-    const int64_t i = cell0 + threadIdx.x;
+    const int64_t i = source_cell(cells, L, cell0 + threadIdx.x);
     CellFM c; c.valid = 0; c.breaks_down = 0; c.detA = 1.0; c.eta_scale = 1.0;
     double sF[4] = {44.0, 0.0, 0.0, 0.0};        // feqmod scalars: 1/T_mod^2, per-cell renorm (Jonah), -, -
     double sL[4] = {0.0, 0.0, 0.0, 0.0};         // linear scalars: K0, K2, K3, -
     double aux[8] = {0, 0, 0, 0, 0, 0, 0, 0};    // per-cell inputs of the (cell, species) renormalisation kernel
-    if (i < cells.n) {
+    if (i >= 0) {
       const double tau = cells.tau[i], tau2 = tau * tau;
       const double ux = cells.ux[i], uy = cells.uy[i], un = cells.un[i];
       const double ut = sqrt(1.0 + ux * ux + uy * uy + tau2 * un * un);
@@ -523,10 +531,10 @@ prepare_vah_kernel(RawCells cells, PrepTables tab, Layout L, int include_shear, 
   __shared__ CellVAH sc_[kPrepCells];
   const int64_t cell0 = (int64_t)blockIdx.x * kPrepCells;
   if (threadIdx.x < kPrepCells) {
-    const int64_t i = cell0 + threadIdx.x;
+    const int64_t i = source_cell(cells, L, cell0 + threadIdx.x);
     CellVAH c; c.valid = 0;
     double s4[4] = {0.0, 0.0, 0.0, 0.0};
-    if (i < cells.n) {
+    if (i >= 0) {
       const double tau = cells.tau[i], tau2 = tau * tau;
       const double ux = cells.ux[i], uy = cells.uy[i], un = cells.un[i];
       const double ut = sqrt(1.0 + ux * ux + uy * uy + tau2 * un * un);

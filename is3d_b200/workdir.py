@@ -133,7 +133,7 @@ def materialize(root, surface_columns=None, chosen=None, fixture=None, tables=No
     fx = fixture if fixture is not None else load_fixture()
     p = {k.lower(): v for k, v in params.items()}
     hrg_eos = int(p.get("hrg_eos", dict(DEFAULT_PARAMETERS)["hrg_eos"]))
-    for d in ("input", "PDG", "tables/eta", "results/vn_continuous", "results/continuous", "results/sampled",
+    for d in ("input", "PDG", "tables/eta", "results/vn_continuous", "results/continuous", "results/sampled", "results/spacetime_distribution",
               "deltaf_coefficients/vh", "deltaf_coefficients/vah"):
         os.makedirs(os.path.join(root, d), exist_ok=True)
     write_parameters(os.path.join(root, "iS3D_parameters.dat"), **params)

@@ -355,6 +355,119 @@ int64_t cfo_smooth_vh(const cfo_flags *fl, const cfo_cells *c, const cfo_species
   return skipped;
 }
 
+/* ---------------------------------------------------------------- N2: spacetime distributions, linear delta-f, :1000-1446 */
+/* the (tau, r) bin of a cell and the histogram updates of :1381-1400 */
+static void spacetime_bin(const cfo_spacetime_spec *spec, double tau, double x, double y, double value,
+                          double *h_tau, double *h_r, double *h_taur)
+{
+  const double tau_width = (spec->tau_max - spec->tau_min) / (double)spec->tau_bins;
+  const double r_width = (spec->r_max - spec->r_min) / (double)spec->r_bins;
+  double r = sqrt(x * x + y * y);
+  int itau = (int)floor((tau - spec->tau_min) / tau_width);
+  int ir = (int)floor((r - spec->r_min) / r_width);
+  if (itau >= 0 && itau < spec->tau_bins) {
+    h_tau[itau] += value;
+    if (ir >= 0 && ir < spec->r_bins) h_taur[(int64_t)itau * spec->r_bins + ir] += value;
+  }
+  if (ir >= 0 && ir < spec->r_bins) h_r[ir] += value;
+}
+
+int64_t cfo_spacetime_vh(const cfo_flags *fl, const cfo_cells *c, const cfo_species *sp, const cfo_grid *g,
+                         const cfo_df_tables *tab, const cfo_spacetime_spec *spec,
+                         double *dN_tau, double *dN_r, double *dN_taur, double *dN_dydeta, double *dN_dy)
+{
+  if (fl->df_mode != 1 && fl->df_mode != 2) return -1;
+  if (fl->include_baryon) return -2;
+  const double prefactor = pow(2.0 * M_PI * hbarC, -3);
+  const int npart = sp->n, npT = g->n_pT, nphi = g->n_phi;
+  int y_pts, eta_pts; grid_dims(fl, g, &y_pts, &eta_pts);
+  const int64_t n = c->n_cells;
+  spline_cache sc; cache_build(&sc, tab);
+  cell_setup *cs = (cell_setup *)malloc(sizeof(cell_setup) * (size_t)(n > 0 ? n : 1));
+  int64_t skipped = 0; int bad = 0;
+  for (int64_t i = 0; i < n; i++) {                      /* per-cell set-up :1146-1283, identical to :118-242 */
+    cell_setup *s = &cs[i];
+    cell_common(fl, c, i, s);
+    if (s->skip) { skipped++; continue; }
+    if (df_eval(&sc, fl->df_mode, s->T, s->E, s->P, s->bulkPi, &s->df)) bad = 1;
+    if (fl->df_mode == 1) {
+      s->shear_coeff = 0.5 / (s->T * s->T * (s->E + s->P));
+      s->bulk0_coeff = s->df.c0 - s->df.c2;
+      s->bulk1_coeff = s->df.c1;
+      s->bulk2_coeff = 4.0 * s->df.c2 - s->df.c0;
+    } else {
+      s->shear_coeff = 0.5 / (s->df.betapi * s->T);
+      s->bulk0_coeff = s->df.F / (s->T * s->T * s->df.betabulk);
+      s->bulk1_coeff = s->df.G / s->df.betabulk;
+      s->bulk2_coeff = 1.0 / (3.0 * s->T * s->df.betabulk);
+    }
+  }
+  cache_free(&sc);
+  if (bad) { free(cs); return -3; }
+  double *cosphi = (double *)malloc(sizeof(double) * nphi), *sinphi = (double *)malloc(sizeof(double) * nphi);
+  for (int k = 0; k < nphi; k++) { cosphi[k] = cos(g->phi[k]); sinphi[k] = sin(g->phi[k]); }
+
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int ipart = 0; ipart < npart; ipart++) {
+    const double mass = sp->mass[ipart], mass2 = mass * mass, sign = sp->sign[ipart];
+    const double degeneracy = sp->degeneracy[ipart], baryon = sp->baryon[ipart];
+    double *h_tau = dN_tau + (int64_t)ipart * spec->tau_bins, *h_r = dN_r + (int64_t)ipart * spec->r_bins;
+    double *h_taur = dN_taur + (int64_t)ipart * spec->tau_bins * spec->r_bins;
+    double *h_eta = dN_dydeta + (int64_t)ipart * eta_pts;
+    for (int64_t icell = 0; icell < n; icell++) {
+      const cell_setup *s = &cs[icell];
+      if (s->skip) continue;
+      const double chem = baryon * s->alphaB;
+      double dN_dy_cell = 0.0;
+      for (int ipT = 0; ipT < npT; ipT++) {
+        const double pT = g->pT[ipT], mT = sqrt(mass2 + pT * pT), mT_over_tau = mT / s->tau;
+        const double pT_weight = spec->pT_weight[ipT];
+        for (int iphip = 0; iphip < nphi; iphip++) {
+          const double px = pT * cosphi[iphip], py = pT * sinphi[iphip], phi_weight = g->phi_weight[iphip];
+          for (int iy = 0; iy < y_pts; iy++) {           /* 3+1D: every y point is summed, without y weights (:1299) */
+            const double y = (fl->dimension == 2) ? 0.0 : g->y[iy];
+            double eta_sum = 0.0;
+            for (int ieta = 0; ieta < eta_pts; ieta++) {
+              const double eta = (fl->dimension == 2) ? g->eta[ieta] : s->eta;
+              const double eta_weight = (fl->dimension == 2) ? g->eta_weight[ieta] : 1.0;
+              const double pt = mT * cosh(y - eta), pn = mT_over_tau * sinh(y - eta), tau2_pn = s->tau2 * pn;
+              const double pdotdsigma = eta_weight * (pt * s->dat + px * s->dax + py * s->day + pn * s->dan);
+              if (fl->outflow && pdotdsigma <= 0.0) continue;
+              const double pdotu = pt * s->ut - px * s->ux - py * s->uy - tau2_pn * s->un;
+              const double feq = 1.0 / (exp(pdotu / s->T - chem) + sign);
+              const double feqbar = 1.0 - sign * feq;
+              const double pimunu_pmu_pnu = s->pitt * pt * pt + s->pixx * px * px + s->piyy * py * py + s->pinn * tau2_pn * tau2_pn
+                + 2.0 * (-(s->pitx * px + s->pity * py) * pt + s->pixy * px * py + tau2_pn * (s->pixn * px + s->piyn * py - s->pitn * pt));
+              const double Vmu_pmu = s->Vt * pt - s->Vx * px - s->Vy * py - s->Vn * tau2_pn;
+              double df;
+              if (fl->df_mode == 1) {
+                const double df_shear = s->shear_coeff * pimunu_pmu_pnu;
+                const double df_bulk = (s->bulk0_coeff * mass2 + (s->bulk1_coeff * baryon + s->bulk2_coeff * pdotu) * pdotu) * s->bulkPi;
+                const double df_diff = (s->df.c3 * baryon + s->df.c4 * pdotu) * Vmu_pmu;
+                df = feqbar * (df_shear + df_bulk + df_diff);
+              } else {
+                const double df_shear = s->shear_coeff * pimunu_pmu_pnu / pdotu;
+                const double df_bulk = (s->bulk0_coeff * pdotu + s->bulk1_coeff * baryon + s->bulk2_coeff * (pdotu - mass2 / pdotu)) * s->bulkPi;
+                const double df_diff = (s->baryon_enthalpy_ratio - baryon / pdotu) * Vmu_pmu / s->df.betaV;
+                df = feqbar * (df_shear + df_bulk + df_diff);
+              }
+              if (fl->regulate_deltaf) df = fmax(-1.0, fmin(df, 1.0));
+              const double f = feq * (1.0 + df);
+              eta_sum += (pdotdsigma * f);
+              h_eta[ieta] += (pT_weight * phi_weight * prefactor * degeneracy * pdotdsigma * f / eta_weight);
+            }
+            dN_dy_cell += (pT_weight * phi_weight * prefactor * degeneracy * eta_sum);
+          }
+        }
+      }
+      dN_dy[ipart] += dN_dy_cell;
+      spacetime_bin(spec, s->tau, spec->x[icell], spec->y[icell], dN_dy_cell, h_tau, h_r, h_taur);
+    }
+  }
+  free(cs); free(cosphi); free(sinphi);
+  return skipped;
+}
+
 /* ---------------------------------------------------------------- a2: modified-equilibrium kernel, :396-996 */
 typedef struct {
   double Xt, Xx, Xy, Xn, Yx, Yy, Zt, Zn;

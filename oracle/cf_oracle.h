@@ -91,6 +91,23 @@ int64_t cfo_smooth_feqmod(const cfo_flags *fl, const cfo_cells *c, const cfo_spe
 /* EmissionFunctionArray::calculate_dN_pTdpTdphidy_VAH_PL, :2140-2393 */
 int64_t cfo_smooth_vah(const cfo_flags *fl, const cfo_cells *c, const cfo_species *sp, const cfo_grid *g, double *dN);
 
+/* operation = 0: spacetime distributions.  x, y are the transverse cell positions; the result arrays are
+ * the RAW sums the reference accumulates before its writers divide by the bin widths (zero-initialised by the caller):
+ *   dN_tau [n_species][tau_bins], dN_r [n_species][r_bins], dN_taur [n_species][tau_bins][r_bins],
+ *   dN_dydeta [n_species][eta_pts] (eta_pts = 1 in 3+1D, n_eta in 2+1D), dN_dy [n_species]. */
+typedef struct {
+  double tau_min, tau_max, r_min, r_max;
+  int32_t tau_bins, r_bins;
+  const double *x, *y;                   /* [n_cells] */
+  const double *pT_weight;               /* [n_pT] */
+} cfo_spacetime_spec;
+
+/* EmissionFunctionArray::calculate_dN_dX, emissionfunction_smooth_kernels.cpp:1000-1446 (df_mode 1,2).
+ * Returns #cells skipped (u.dsigma <= 0) or a negative error code. */
+int64_t cfo_spacetime_vh(const cfo_flags *fl, const cfo_cells *c, const cfo_species *sp, const cfo_grid *g,
+                         const cfo_df_tables *tab, const cfo_spacetime_spec *spec,
+                         double *dN_tau, double *dN_r, double *dN_taur, double *dN_dydeta, double *dN_dy);
+
 /* VAH helpers: aL_fit / R200 (arsenal.cpp:999-1066) and the (Lambda, aL) bilinear lookup of
  * src/cuda/deltafReader.cu:192-277 */
 double cfo_aL_fit(double pl_over_peq);

@@ -44,6 +44,11 @@ class DfTables(C.Structure):
                [("n_jonah", C.c_int32), ("jonah_x", _D), ("jonah_lambda2", _D), ("jonah_z", _D), ("bulkPi_over_Peq_max", C.c_double)]
 
 
+class SpacetimeSpec(C.Structure):
+    _fields_ = [("tau_min", C.c_double), ("tau_max", C.c_double), ("r_min", C.c_double), ("r_max", C.c_double),
+                ("tau_bins", C.c_int32), ("r_bins", C.c_int32), ("x", _D), ("y", _D), ("pT_weight", _D)]
+
+
 class Laguerre(C.Structure):
     _fields_ = [("n_points", C.c_int32), ("root1", _D), ("weight1", _D), ("root2", _D), ("weight2", _D)]
 
@@ -62,6 +67,7 @@ def lib():
         L.cfo_smooth_vh.restype = C.c_int64
         L.cfo_smooth_feqmod.restype = C.c_int64
         L.cfo_smooth_vah.restype = C.c_int64
+        L.cfo_spacetime_vh.restype = C.c_int64
         L.cfo_jonah_tables.restype = C.c_double
         L.cfo_aL_fit.restype = C.c_double; L.cfo_aL_fit.argtypes = [C.c_double]
         L.cfo_R200.restype = C.c_double; L.cfo_R200.argtypes = [C.c_double]
@@ -175,6 +181,48 @@ def smooth(flags, cells, species, grid, tables=None, laguerre=None, vah=False, c
     if rc < 0:
         raise RuntimeError("cf_oracle error %d" % rc)
     return dN, int(rc), int(bd.value)
+
+
+def spacetime(flags, cells, species, grid, tables, bins, laguerre=None):
+    """operation = 0 oracle.  cells must carry "x" and "y"; bins = dict(tau_min, tau_max, tau_bins, r_min, r_max, r_bins).
+
+    Returns (dict of raw sums dN_tau [s][tau], dN_r [s][r], dN_taur [s][tau][r], dN_dydeta [s][eta_pts], dN_dy [s]), skipped."""
+    keep = _Keep()
+    ns = len(species["mass"]); nt = int(bins["tau_bins"]); nr = int(bins["r_bins"])
+    eta_pts = len(grid["eta"]) if flags["dimension"] == 2 else 1
+    out = dict(dN_tau=np.zeros((ns, nt)), dN_r=np.zeros((ns, nr)), dN_taur=np.zeros((ns, nt, nr)),
+               dN_dydeta=np.zeros((ns, eta_pts)), dN_dy=np.zeros(ns))
+    spec = SpacetimeSpec()
+    spec.tau_min, spec.tau_max, spec.r_min, spec.r_max = (float(bins[k]) for k in ("tau_min", "tau_max", "r_min", "r_max"))
+    spec.tau_bins, spec.r_bins = nt, nr
+    spec.x = keep.arr(cells["x"]); spec.y = keep.arr(cells["y"]); spec.pT_weight = keep.arr(grid["pT_weight"])
+    fl = _flags(flags); c = _cells(keep, cells); sp = _species(keep, species); g = _grid(keep, grid)
+    t = _tables(keep, tables)
+    if flags["df_mode"] in (1, 2):
+        rc = lib().cfo_spacetime_vh(C.byref(fl), C.byref(c), C.byref(sp), C.byref(g), C.byref(t), C.byref(spec),
+                                    _p(out["dN_tau"]), _p(out["dN_r"]), _p(out["dN_taur"]), _p(out["dN_dydeta"]), _p(out["dN_dy"]))
+    else:
+        raise NotImplementedError("spacetime oracle: df_mode %d" % flags["df_mode"])
+    if rc < 0:
+        raise RuntimeError("cf_oracle error %d" % rc)
+    return out, int(rc)
+
+
+def read_spacetime_files(workdir, mcid, bins, eta_pts):
+    """Parse results/spacetime_distribution/*_<mcid>.dat as the reference writes them (smooth_kernels.cpp:1404-1435) and undo
+    the bin-width normalisation -> the same raw sums as spacetime() (7 significant digits)."""
+    nt = int(bins["tau_bins"]); nr = int(bins["r_bins"])
+    tw = (bins["tau_max"] - bins["tau_min"]) / nt; rw = (bins["r_max"] - bins["r_min"]) / nr
+    d = os.path.join(workdir, "results", "spacetime_distribution")
+    a = np.loadtxt(os.path.join(d, "dN_taudtaudy_%d.dat" % mcid), ndmin=2)
+    b = np.loadtxt(os.path.join(d, "dN_twopirdrdy_%d.dat" % mcid), ndmin=2)
+    c = np.loadtxt(os.path.join(d, "dN_twopitaurdtaudrdy_%d.dat" % mcid), ndmin=2)
+    e = np.loadtxt(os.path.join(d, "dN_dydeta_%d_%dpt.dat" % (mcid, eta_pts)), ndmin=2)
+    tau_mid = bins["tau_min"] + tw * (np.arange(nt) + 0.5); r_mid = bins["r_min"] + rw * (np.arange(nr) + 0.5)
+    out = dict(dN_tau=a[:, 1] * tau_mid * tw, dN_r=b[:, 1] * 2.0 * np.pi * r_mid * rw,
+               dN_taur=(c[:, 2].reshape(nr, nt) * (2.0 * np.pi * tw * rw) * r_mid[:, None] * tau_mid[None, :]).T,
+               dN_dydeta=e[:, 1], eta_column=e[:, 0], tau_mid=a[:, 0], r_mid=b[:, 0])
+    return out
 
 
 # --------------------------------------------------------------------------- compiled reference (oracle/_ref)
