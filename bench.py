@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--operation", type=int, default=1, choices=[0, 1],
+                    help="1: momentum spectra (headline); 0: spacetime distributions of the same integrand (SURVEY 8f N2), df_mode 1-4 workloads")
     ap.add_argument("--cells", type=int, default=0, help="override the cell count (development only; reported in config)")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -104,7 +106,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm / CPU baseline
-def reference_sample(workload, cells=4000, n_species=4, threads=None, repeats=1):
+SPACETIME_BINS = dict(tau_min=0.0, tau_max=12.0, tau_bins=120, r_min=0.0, r_max=12.0, r_bins=60)      # iS3D_parameters.dat:82-89
+
+
+def reference_sample(workload, cells=4000, n_species=4, threads=None, repeats=1, operation=1):
     """Time the unmodified reference (OpenMP build, all host cores) on a bounded sample of the workload.
 
     Returns dict(value evals/s, cores, kind, sample, seconds list).  Falls back to the C oracle ("port") if the reference
@@ -116,6 +121,8 @@ def reference_sample(workload, cells=4000, n_species=4, threads=None, repeats=1)
     threads = threads or os.cpu_count() or 1
     if dim == 2:
         cells = max(cells // 20, 50)
+    if operation == 0:
+        cells = max(cells // 4, 20)                # calculate_dN_dX has no OpenMP pragma: one core whatever OMP_NUM_THREADS says
     cols = synthetic.surface_vh(cells, synthetic.SEEDS["cfg3" if dim == 3 else "cfg2"], three_d=(dim == 3), viscous=viscous)
     ids = list(fx[chosen][:n_species])
     sp = tables.species(fx, 1, ids); g = tables.grid(fx)
@@ -125,16 +132,20 @@ def reference_sample(workload, cells=4000, n_species=4, threads=None, repeats=1)
     if exe is not None:
         wd = tempfile.mkdtemp(prefix="is3d_ref_")
         try:
-            workdir.materialize(wd, surface_columns=cols, chosen=ids, fixture=fx, operation=1, mode=1, hrg_eos=1, dimension=dim,
-                                df_mode=dfm, include_bulk_deltaf=int(viscous), include_shear_deltaf=int(viscous))
+            workdir.materialize(wd, surface_columns=cols, chosen=ids, fixture=fx, operation=operation, mode=1, hrg_eos=1, dimension=dim,
+                                df_mode=dfm, include_bulk_deltaf=int(viscous), include_shear_deltaf=int(viscous), **SPACETIME_BINS)
             for _ in range(repeats):
-                _, info = cfo.run_reference(wd, what="kernel", omp=True, threads=threads)
+                _, info = cfo.run_reference(wd, what="kernel" if operation == 1 else "full", omp=True, threads=threads)
                 secs.append(info["seconds"])
         finally:
             shutil.rmtree(wd, ignore_errors=True)
         kind = "reference"
         note = "unmodified reference src/cpp, g++ -O3 -fopenmp (CMakeLists.txt:11), OMP_NUM_THREADS=%d, kernel call only" % threads
-        if dim == 3:
+        if operation == 0:
+            note = "unmodified reference src/cpp, g++ -O3 -fopenmp, calculate_spectra() with operation = 0 incl. its file writers; " \
+                   "calculate_dN_dX has no OpenMP pragma, so it runs on 1 core"
+            threads = 1
+        elif dim == 3:
             note += "; timing only: the reference's 3+1D OpenMP results are wrong (data race, SURVEY R3)"
     else:
         cells_soa = synthetic.columns_to_cells(cols, 1)
@@ -142,7 +153,12 @@ def reference_sample(workload, cells=4000, n_species=4, threads=None, repeats=1)
         fl = tables.flags(df_mode=dfm, dimension=dim, include_bulk=int(viscous), include_shear=int(viscous))
         os.environ["OMP_NUM_THREADS"] = str(threads)
         for _ in range(repeats):
-            t0 = time.perf_counter(); cfo.smooth(fl, cells_soa, sp, g, tab, gla); secs.append(time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            if operation == 0:
+                cfo.spacetime(fl, cells_soa, sp, g, tab, SPACETIME_BINS, gla)
+            else:
+                cfo.smooth(fl, cells_soa, sp, g, tab, gla)
+            secs.append(time.perf_counter() - t0)
         kind = "port"
         note = "oracle/cf_oracle.c (OpenMP over species, %d threads)" % threads
     best = min(secs)
@@ -158,7 +174,9 @@ def run_reference_arm(args):
     n_full, dim, dfm, chosen, viscous, desc = WORKLOADS[args.workload]
     total = args.steps + args.warmup
     t0 = time.perf_counter()
-    res = reference_sample(args.workload, repeats=total)
+    res = reference_sample(args.workload, repeats=total, operation=args.operation)
+    if args.operation == 0:
+        desc += "; operation = 0: spacetime distributions (120 tau x 60 r bins)"
     secs = res["seconds"][args.warmup:]
     mean = sum(secs) / len(secs)
     value = res["evaluations"] / mean
@@ -217,6 +235,12 @@ def main():
         avg = api.surface_averages(cells)
         tab.update(api.jonah_tables(pdg["mass"], pdg["gspin"].astype(float), pdg["sign"].astype(float), avg[0], gla))
     keys = ["tau", "eta", "dat", "dax", "day", "dan", "ux", "uy", "un", "T", "P", "E", "pixx", "pixy", "pixn", "piyy", "piyn", "bulkPi"]
+    spacetime = (args.operation == 0)
+    if spacetime:
+        if vah:
+            raise SystemExit("operation = 0 has no anisotropic-hydro routine in the reference")
+        keys += ["x", "y"]
+        desc += "; operation = 0: spacetime distributions (120 tau x 60 r bins)"
     if vah:
         keys += ["pitt", "pitx", "pity", "pitn", "pinn", "Wx", "Wy", "Lambda", "aL", "c0", "c1", "c2", "c3", "c4"]
     lo, hi = distributed.shard_bounds(n_cells, rank, world)
@@ -230,7 +254,22 @@ def main():
     out = torch.zeros(n_bins, dtype=torch.float64, device="cuda")
     stream = torch.cuda.current_stream()
 
+    st_keys = ("dN_tau", "dN_r", "dN_taur", "dN_dydeta", "dN_dy")
+    last = {}
+
+    def spacetime_step(cells_arg, memory):
+        res, st = api.spacetime_distributions(fl, cells_arg, sp, g, tab, gla, SPACETIME_BINS, memory=memory, tile_variant=args.variant)
+        flat = np.concatenate([res[k].ravel() for k in st_keys])
+        if world > 1:                                  # the histograms are linear in the cells: one all-reduce of the raw sums
+            t = torch.from_numpy(flat).cuda()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            flat = t.cpu().numpy()
+        last["flat"] = flat; last["dN_dy"] = flat[-len(sp["mass"]):]
+        return st
+
     def step_device():
+        if spacetime:
+            return spacetime_step(dev, "device")
         out.zero_()
         _, st = api.smooth_spectra(fl, dev, sp, g, tab, gla, out=out, memory="device", tile_variant=args.variant)
         if world > 1:
@@ -272,7 +311,7 @@ def main():
         kernel_mean = sum(kernel_ms) / len(kernel_ms)
     ms_step = ms_total / args.steps
     value = evals_step / (ms_step * 1e-3)
-    checksum = float(out.sum().item())
+    checksum = float(last["dN_dy"].sum()) if spacetime else float(out.sum().item())
 
     # ---- end to end through the C ABI with host buffers
     e2e = None
@@ -281,6 +320,9 @@ def main():
         pinned_out = torch.zeros(n_bins, dtype=torch.float64).pin_memory()
 
         def step_host():
+            if spacetime:                              # host arrays in, host histograms out (H2D of the shard + D2H inside the call)
+                spacetime_step(host_np, "host")
+                return last["dN_dy"]
             if world == 1:
                 host_out[:] = 0.0
                 api.smooth_spectra(fl, host_np, sp, g, tab, gla, out=host_out, tile_variant=args.variant)
@@ -304,7 +346,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": evals_step / (dt / args.steps), "unit": "evaluations/s",
-               "h2d_bytes_per_step": int(len(keys) * 8 * n_cells), "d2h_bytes_per_step": int(n_bins * 8 * world),
+               "h2d_bytes_per_step": int(len(keys) * 8 * n_cells), "d2h_bytes_per_step": int((last["flat"].size if spacetime else n_bins) * 8 * world),
                "checksum_rel_diff": abs(float(np.sum(res)) - checksum) / abs(checksum) if checksum else 0.0}
 
     if rank != 0:
@@ -330,17 +372,21 @@ def main():
         try:
             if vah:
                 raise RuntimeError("the reference cannot run this configuration: its anisotropic kernel is dead code (SURVEY R1)")
-            r = reference_sample(args.workload)
+            r = reference_sample(args.workload, operation=args.operation)
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:          # the baseline is a reported number, never a reason to lose the GPU measurement
             cpu = {"value": None, "unit": "evaluations/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (e,)}
 
+    if spacetime:
+        evals_2d = 2 if dim == 2 else 1               # 2+1D runs the integrand twice (binned yield + per-eta rapidity distribution)
+        roofline["note"] = "operation = 0: same hot kernel with the momentum-integrated epilogue%s; evaluations counted once" % (
+            " launched twice in 2+1D" if evals_2d == 2 else "")
     line = {
         "metric": "Cooper-Frye cell*momentum*species evaluations/s", "value": value, "unit": "evaluations/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "cells": n_cells, "species": len(sp["mass"]), "momentum_bins": len(g["pT"]) * len(g["phi"]) * len(g["y"]),
-                   "evaluations_per_step": evals_step, "sharding": "cells split contiguously over %d rank(s), one all-reduce of %d doubles" % (world, n_bins),
+                   "evaluations_per_step": evals_step, "sharding": "cells split contiguously over %d rank(s), one all-reduce of %d doubles" % (world, last["flat"].size if spacetime else n_bins),
                    "l2": "inputs larger than L2: %.0f MB of raw cell arrays + %.0f MB of per-cell records per rank vs 126 MB L2"
                          % (len(keys) * 8 * (hi - lo) / 1e6, rec_bytes / 1e6),
                    "tile_variant": args.variant, "underflow_skip": "evaluations whose exp(u.p/T) overflows (f = 0 exactly in the reference) are skipped; they still count as evaluations",

@@ -40,6 +40,8 @@ typedef struct {
   const double *muB, *nB, *Vx, *Vy, *Vn;
   /* anisotropic hydro (mode 2) only: all ten pi_perp components, W_perp, Lambda, alpha_L and per-cell c0..c4 */
   const double *pitt, *pitx, *pity, *pitn, *pinn, *Wx, *Wy, *Lambda, *aL, *c0, *c1, *c2, *c3, *c4;
+  /* transverse cell positions: read by operation = 0 (spacetime distributions) only, NULL otherwise */
+  const double *x, *y;
 } is3d_surface;
 
 /* Chosen species in output order (emissionfunction.cpp:1293-1307). */
@@ -115,7 +117,7 @@ int is3d_b200_smooth_spectra(const is3d_flags *flags, const is3d_surface *surfac
  * Replaces EmissionFunctionArray::calculate_dN_dX (emissionfunction_smooth_kernels.cpp:1000-1446, df_mode 1, 2) and
  * calculate_dN_dX_feqmod (:1449-2135, df_mode 3, 4), called from calculate_spectra (emissionfunction.cpp:1514, 1579).
  * Every cell's yield  sum_{pT, phi, y} w_pT w_phi g/(2 pi hbar c)^3 sum_eta p.dsigma f  (3+1D: all y points, unweighted,
- * like the reference) is binned by the cell's tau and r = sqrt(x^2 + y^2):
+ * like the reference) is binned by the cell's tau and r = sqrt(x^2 + y^2) (is3d_surface.x, .y):
  *    itau = floor((tau - tau_min) / ((tau_max - tau_min) / tau_bins)),  ir likewise (:1376-1400).
  * Results are the RAW sums the reference accumulates; its writers divide by the bin volumes (:1404-1435), see
  * is3d_b200_write_spacetime().  Arrays are caller-allocated host memory and are OVERWRITTEN:
@@ -124,7 +126,6 @@ int is3d_b200_smooth_spectra(const is3d_flags *flags, const is3d_surface *surfac
 typedef struct {
   double tau_min, tau_max, r_min, r_max;   /* iS3D_parameters.dat: tau_min, tau_max, r_min, r_max */
   int32_t tau_bins, r_bins;                /* tau_bins, r_bins */
-  const double *x, *y;                     /* [n_cells] transverse cell positions, same memory space as the surface arrays */
   const double *pT_weight, *phi_weight;    /* host: second column of the pT and phi tables */
 } is3d_spacetime_bins;
 typedef struct { double *dN_tau, *dN_r, *dN_taur, *dN_dydeta, *dN_dy; } is3d_spacetime_result;
@@ -142,7 +143,10 @@ int is3d_b200_measure_fp64_sustained(double seconds, double *tflops);
 /* ---- host layer: the drop-in behind iS3D_parameters.dat / input/surface.dat / PDG / deltaf_coefficients / tables ----
  * Equivalent of IS3D::run_particlization(1) with operation = 1 (src/cpp/iS3D.cpp:73-191): reads the CWD-relative input
  * files under `workdir`, runs the spectra on the GPU, writes results/dN_pTdpTdphidy*.dat, results/vn_continuous/ and
- * results/dN_dy_*.dat with the reference's formats.  If dN_raw != NULL it receives the spectra (n_raw doubles max). */
+ * results/dN_dy_*.dat with the reference's formats.  If dN_raw != NULL it receives the spectra (n_raw doubles max).
+ * operation = 0 runs the spacetime distributions instead and writes results/spacetime_distribution/dN_taudtaudy_<mcid>.dat,
+ * dN_twopirdrdy_<mcid>.dat, dN_twopitaurdtaudrdy_<mcid>.dat, dN_dydeta_<mcid>_<eta_pts>pt.dat (smooth_kernels.cpp:1112-1126,
+ * 1404-1435); dN_raw then receives the raw sums concatenated as [dN_tau | dN_r | dN_taur | dN_dydeta | dN_dy]. */
 int is3d_b200_run_workdir(const char *workdir, double *dN_raw, int64_t n_raw, int32_t *mcid_out, int32_t n_mcid_max,
                           is3d_stats *stats);
 /* Same with the freeze-out cells passed in memory (reference: IS3D::read_fo_surf_from_memory + run_particlization(0),

@@ -15,7 +15,7 @@ _D = C.POINTER(C.c_double)
 
 SURFACE_FIELDS = ("tau", "eta", "dat", "dax", "day", "dan", "ux", "uy", "un", "T", "P", "E",
                   "pixx", "pixy", "pixn", "piyy", "piyn", "bulkPi", "muB", "nB", "Vx", "Vy", "Vn",
-                  "pitt", "pitx", "pity", "pitn", "pinn", "Wx", "Wy", "Lambda", "aL", "c0", "c1", "c2", "c3", "c4")
+                  "pitt", "pitx", "pity", "pitn", "pinn", "Wx", "Wy", "Lambda", "aL", "c0", "c1", "c2", "c3", "c4", "x", "y")
 DF_FIELDS = ("T", "c0", "c1", "c2", "c3", "c4", "F", "G", "betabulk", "betaV", "betapi")
 
 ERRORS = {0: "IS3D_OK", 1: "IS3D_ERR_ARGUMENT", 2: "IS3D_ERR_UNSUPPORTED", 3: "IS3D_ERR_TABLE_RANGE", 4: "IS3D_ERR_CUDA",
@@ -278,7 +278,7 @@ def smooth_spectra(flags, cells, species, grid, df_tables=None, laguerre=None, o
 
 class SpacetimeBins(C.Structure):
     _fields_ = [("tau_min", C.c_double), ("tau_max", C.c_double), ("r_min", C.c_double), ("r_max", C.c_double),
-                ("tau_bins", C.c_int32), ("r_bins", C.c_int32), ("x", _D), ("y", _D), ("pT_weight", _D), ("phi_weight", _D)]
+                ("tau_bins", C.c_int32), ("r_bins", C.c_int32), ("pT_weight", _D), ("phi_weight", _D)]
 
 
 class SpacetimeResult(C.Structure):
@@ -298,7 +298,8 @@ def spacetime_distributions(flags, cells, species, grid, df_tables, laguerre, bi
     b = SpacetimeBins()
     b.tau_min, b.tau_max, b.r_min, b.r_max = (float(bins[k]) for k in ("tau_min", "tau_max", "r_min", "r_max"))
     b.tau_bins, b.r_bins = int(bins["tau_bins"]), int(bins["r_bins"])
-    b.x = m.cells(cells["x"]); b.y = m.cells(cells["y"])
+    if cells.get("x") is None or cells.get("y") is None:
+        raise KeyError("spacetime_distributions needs the transverse cell positions cells['x'], cells['y']")
     b.pT_weight = m.host(grid["pT_weight"]); b.phi_weight = m.host(grid["phi_weight"])
     ns = sp.n; eta_pts = g.n_eta if flags["dimension"] == 2 else 1
     out = dict(dN_tau=np.zeros((ns, b.tau_bins)), dN_r=np.zeros((ns, b.r_bins)), dN_taur=np.zeros((ns, b.tau_bins, b.r_bins)),

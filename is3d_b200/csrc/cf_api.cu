@@ -237,6 +237,7 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   L.n_species = sp->n; L.n_pT = gr->n_pT; L.n_phi = gr->n_phi; L.n_y_out = gr->n_y;
   L.dim2 = dim2 ? 1 : 0;
   L.per_slot = (iq && iq->mode == 2) ? 1 : 0;
+  L.dx = iq ? 1 : 0;
   L.n_slots = dim2 ? gr->n_eta : gr->n_y;
   L.rec_y = vah ? kRecVah : kRec;
   const bool sum_slots = dim2 && !L.per_slot;               // the hot kernel folds the eta slots into one accumulator
@@ -571,19 +572,19 @@ extern "C" int is3d_b200_spacetime_distributions(const is3d_flags *fl, const is3
   if ((int64_t)(bins->tau_bins + 1) * (bins->r_bins + 1) > (1 << 24)) return fail(IS3D_ERR_ARGUMENT, "too many (tau, r) bins");
   const int64_t n = sf->n_cells;
   if (n < 0) return fail(IS3D_ERR_ARGUMENT, "negative cell count");
-  if (n > 0 && (!sf->tau || !bins->x || !bins->y)) return fail(IS3D_ERR_ARGUMENT, "tau, x, y arrays are required");
+  if (n > 0 && (!sf->tau || !sf->x || !sf->y)) return fail(IS3D_ERR_ARGUMENT, "tau, x, y arrays are required");
   if (fl->mode == 2) return fail(IS3D_ERR_UNSUPPORTED, "spacetime distributions exist for mode 1 surfaces only");
   const bool device_mem = opt_in && opt_in->memory == 1;
   if (!g_init) { int rc = is3d_b200_init(); if (rc) return rc; }
 
   // ---- (tau, r) category of every cell on the host (:1376-1379); index tau_bins / r_bins = outside the histogram
   std::vector<double> hbuf;
-  const double *tau = sf->tau, *x = bins->x, *y = bins->y;
+  const double *tau = sf->tau, *x = sf->x, *y = sf->y;
   if (device_mem && n > 0) {
     hbuf.resize((size_t)n * 3);
     if (cudaMemcpy(hbuf.data(), sf->tau, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
-        cudaMemcpy(hbuf.data() + n, bins->x, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
-        cudaMemcpy(hbuf.data() + 2 * n, bins->y, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+        cudaMemcpy(hbuf.data() + n, sf->x, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(hbuf.data() + 2 * n, sf->y, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
       return fail(IS3D_ERR_CUDA, "device -> host copy of tau, x, y failed");
     tau = hbuf.data(); x = tau + n; y = x + n;
   }

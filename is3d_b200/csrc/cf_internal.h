@@ -43,6 +43,7 @@ struct Layout {
   int n_slots;                           // rapidity slots per cell: n_y (3+1D) or n_eta (2+1D)
   int dim2;                              // dimension == 2: slots are the eta table (y = 0), else the y table at the cell's eta
   int per_slot;                          // dim2 only: keep the eta slots apart (3+1D-shaped tiles) instead of summing them
+  int dx;                                // feqmod set-up follows calculate_dN_dX_feqmod (operation = 0) where it differs from the spectra routine
   int nst, n_ytiles, npt, n_ptiles;
   int rec_y;                             // doubles per slot record (kRec or kRecVah)
   int ct;                                // cells per TMA tile

@@ -297,8 +297,13 @@ prepare_feqmod_kernel(RawCells cells, PrepTables tab, Layout L, int include_shea
         double bulkPi = include_bulk ? cells.bulkPi[i] : 0.0;
         if (DFM == 4) {                                               // :588-594
           const double mx = tab.bulkPi_over_Peq_max;
-          if (bulkPi < -Pr) bulkPi = -(1.0 - 1.e-5) * Pr;
-          else if (bulkPi / Pr > mx) bulkPi = Pr * (mx - 1.e-5);
+          if (L.dx) {                                                 // calculate_dN_dX_feqmod compares with <=, >= (:1709-1710)
+            if (bulkPi <= -Pr) bulkPi = -(1.0 - 1.e-5) * Pr;
+            else if (bulkPi / Pr >= mx) bulkPi = Pr * (mx - 1.e-5);
+          } else {
+            if (bulkPi < -Pr) bulkPi = -(1.0 - 1.e-5) * Pr;
+            else if (bulkPi / Pr > mx) bulkPi = Pr * (mx - 1.e-5);
+          }
         }
         bool bad = false;
         const double T4 = T * T * T * T;
@@ -360,7 +365,7 @@ prepare_feqmod_kernel(RawCells cells, PrepTables tab, Layout L, int include_shea
           c.piyy = piyy; c.piyn = piyn; c.pinn = pinn;
           c.Xt = Xt; c.Xx = Xx; c.Xy = Xy; c.Xn = Xn; c.Yx = Yx; c.Yy = Yy; c.Zt = Zt; c.Zn = Zn;
           c.invT = 1.0 / T; c.invTmod = 1.0 / T_mod; c.detA = detA;
-          if (detA > tab.deta_min && detA < 1.0 && L.dim2) c.eta_scale = detA;      // :728-729
+          if (detA > tab.deta_min && (L.dx || detA < 1.0) && L.dim2) c.eta_scale = detA;      // :728-729; :1850-1853 has no detA < 1 test
           // linear-branch coefficients (:641-644 / :868-869), written in terms of x = u.p / T
           const double shear_coeff = 0.5 / (betapi * T);
           c.scl = shear_coeff / T;
@@ -374,10 +379,12 @@ prepare_feqmod_kernel(RawCells cells, PrepTables tab, Layout L, int include_shea
           // renormalisation: Jonah z / detA per cell; Mike per (cell, species) in renorm_kernel
           double rn = 1.0;
           if (include_bulk && DFM == 4) rn = z;
+          if (L.dx && (isnan(rn / detA) || isinf(rn / detA))) rn = 0.0;     // :1887 tests renorm / detA in 2+1D too
           if (!L.dim2) rn /= detA;                                   // :780-784 (DIMENSION == 3)
           if (isnan(rn) || isinf(rn)) rn = 0.0;                      // the reference skips the species (:773-778)
           sF[1] = fabs(rn);
           aux[0] = T; aux[1] = T_mod; aux[2] = bulkPi / betabulk; aux[3] = F; aux[4] = (L.dim2 ? 1.0 : detA); aux[5] = 1.0;
+          aux[6] = L.dx ? detA : 1.0;
         }
       }
     }
@@ -408,14 +415,15 @@ prepare_feqmod_kernel(RawCells cells, PrepTables tab, Layout L, int include_shea
     if (L.dim2) { yv = 0.0; eta = tab.slot_y[j]; wgt = tab.slot_w[j]; }
     else        { yv = tab.slot_y[j]; eta = c.eta; wgt = 1.0; }
     bool linear = c.breaks_down != 0;
-    if (!linear && !L.dim2 && c.detA < 0.01 && fabs(yv - eta) < c.detA) {      // narrow breakdown, :813-819
+    if (!linear && !L.dim2 && !L.dx && c.detA < 0.01 && fabs(yv - eta) < c.detA) {      // narrow breakdown, :813-819 (commented out at :1927-1935)
       linear = true;
       atomicAdd(&counters->linear_items, 1ULL);
     }
     if (linear) {
       const double ch = cosh(yv - eta), sh = sinh(yv - eta), tsh = c.tau * sh;
       rl[0] = (ch * c.ut - tsh * c.un) * c.invT;
-      rl[1] = wgt * (ch * c.dat) + (sh * c.inv_tau) * c.dan;                   // eta weight not on the dsigma_eta term (:831)
+      rl[1] = L.dx ? wgt * (ch * c.dat + (sh * c.inv_tau) * c.dan)               // :1948
+                   : wgt * (ch * c.dat) + (sh * c.inv_tau) * c.dan;              // eta weight not on the dsigma_eta term (:831)
       rl[2] = c.scl * (c.pitt * ch * ch + c.pinn * tsh * tsh - 2.0 * c.pitn * tsh * ch);
       rl[3] = ch; rl[4] = tsh; rl[5] = wgt;
     } else {
@@ -427,7 +435,8 @@ prepare_feqmod_kernel(RawCells cells, PrepTables tab, Layout L, int include_shea
       solve_refined3(c.A, c.Ainv, Vv, sol);
       const double v0 = sol[0] * c.invTmod, v1 = sol[1] * c.invTmod, v2 = sol[2] * c.invTmod;
       rf[0] = v0; rf[1] = v1; rf[2] = v2; rf[3] = v0 * v0 + v1 * v1 + v2 * v2;
-      rf[4] = wgt * (ch * c.dat) + (sh * c.inv_tau) * c.dan;                   // :884
+      rf[4] = L.dx ? wgt * (ch * c.dat + (sh * c.inv_tau) * c.dan)               // :2001
+                   : wgt * (ch * c.dat) + (sh * c.inv_tau) * c.dan;              // :884
       rf[5] = wgt;
     }
   }
@@ -488,7 +497,7 @@ __global__ void renorm_mike_kernel(const double *__restrict__ cellaux, int64_t n
       const double n_mod = nmod_fact * g * gl_neq(tab.gla_root1, tab.gla_w1, tab.gla_n, mbar_mod, 0.0, b, sg);
       rn = n_linear / n_mod;
     }
-    if (isnan(rn) || isinf(rn)) rn = 0.0;
+    if (isnan(rn) || isinf(rn) || isnan(rn / a[6]) || isinf(rn / a[6])) rn = 0.0;     // a[6] = detA for the spacetime variant, else 1
     else { rn /= a[4]; rn = fabs(rn); }
   }
   renorm[(int64_t)s * n_cells_pad + i] = rn;

@@ -114,6 +114,39 @@ static bool write_spectra_files(const std::string &wd, const std::vector<double>
   return true;
 }
 
+// results/spacetime_distribution/*.dat exactly as calculate_dN_dX{,_feqmod} write them (smooth_kernels.cpp:1112-1126, 1404-1435):
+// truncating opens, `setprecision(6) << scientific`, bin midpoints, sums divided by the bin volumes.
+static bool write_spacetime_files(const std::string &wd, const std::vector<int> &mcid, const is3d_spacetime_bins &b, int eta_pts,
+                                  const std::vector<double> &eta_values, const std::vector<double> &dN_tau, const std::vector<double> &dN_r,
+                                  const std::vector<double> &dN_taur, const std::vector<double> &dN_dydeta, std::string *err)
+{
+  const int nt = b.tau_bins, nr = b.r_bins;
+  const double tw = (b.tau_max - b.tau_min) / (double)nt, rw = (b.r_max - b.r_min) / (double)nr;
+  std::vector<double> tau_mid(nt), r_mid(nr);
+  for (int i = 0; i < nt; i++) tau_mid[i] = b.tau_min + tw * ((double)i + 0.5);
+  for (int i = 0; i < nr; i++) r_mid[i] = b.r_min + rw * ((double)i + 0.5);
+  const std::string dir = wd + "/results/spacetime_distribution/";
+  for (size_t s = 0; s < mcid.size(); s++) {
+    char n1[64], n2[64], n3[64], n4[96];
+    std::snprintf(n1, sizeof(n1), "dN_taudtaudy_%d.dat", mcid[s]);
+    std::snprintf(n2, sizeof(n2), "dN_twopirdrdy_%d.dat", mcid[s]);
+    std::snprintf(n3, sizeof(n3), "dN_twopitaurdtaudrdy_%d.dat", mcid[s]);
+    std::snprintf(n4, sizeof(n4), "dN_dydeta_%d_%dpt.dat", mcid[s], eta_pts);
+    std::ofstream ft(dir + n1, std::ios_base::out), fr(dir + n2, std::ios_base::out), ftr(dir + n3, std::ios_base::out), fe(dir + n4, std::ios_base::out);
+    if (!ft || !fr || !ftr || !fe) { *err = "cannot write into " + dir + " (the directory must exist, cleanMakeCPU.sh)"; return false; }
+    const double *ht = &dN_tau[s * nt], *hr = &dN_r[s * nr], *htr = &dN_taur[s * (size_t)nt * nr], *he = &dN_dydeta[s * (size_t)eta_pts];
+    for (int ir = 0; ir < nr; ir++) {
+      fr << std::setprecision(6) << std::scientific << r_mid[ir] << "\t" << hr[ir] / (2.0 * M_PI * r_mid[ir] * rw) << "\n";
+      for (int it = 0; it < nt; it++)
+        ftr << std::setprecision(6) << std::scientific << tau_mid[it] << "\t" << r_mid[ir] << "\t"
+            << htr[(size_t)it * nr + ir] / (2.0 * M_PI * tau_mid[it] * r_mid[ir] * tw * rw) << "\n";
+    }
+    for (int it = 0; it < nt; it++) ft << std::setprecision(6) << std::scientific << tau_mid[it] << "\t" << ht[it] / (tau_mid[it] * tw) << "\n";
+    for (int j = 0; j < eta_pts; j++) fe << std::setprecision(6) << std::scientific << eta_values[j] << "\t" << he[j] << "\n";
+  }
+  return true;
+}
+
 // everything the host layer derives from the input files
 struct Problem {
   Params par;
@@ -153,7 +186,8 @@ static int load_problem(const std::string &wd, bool need_surface, Problem *p, st
   fl.regulate_deltaf = (int)par.get("regulate_deltaf", &err);
   fl.outflow = (int)par.get("outflow", &err);
   fl.deta_min = par.get("deta_min", &err); fl.mass_pion0 = par.get("mass_pion0", &err);
-  if (p->operation != 1) { err = "this drop-in covers operation = 1 (smooth momentum spectra) only"; return IS3D_ERR_UNSUPPORTED; }
+  if (p->operation != 1 && p->operation != 0) { err = "this drop-in covers operation = 1 (smooth momentum spectra) and operation = 0 (spacetime distributions); the sampler (operation = 2) is out of scope"; return IS3D_ERR_UNSUPPORTED; }
+  if (p->operation == 0 && fl.mode == 2) { err = "operation = 0 has no anisotropic-hydro routine in the reference (emissionfunction.cpp:1644-1673)"; return IS3D_ERR_UNSUPPORTED; }
   if ((int)par.get("do_resonance_decays", &err)) { err = "do_resonance_decays = 1 is outside the smooth-spectra path"; return IS3D_ERR_UNSUPPORTED; }
 
   // ---- surface (+ averages side file)
@@ -219,6 +253,35 @@ static int run_problem(const std::string &wd, Problem &P, const is3d_surface &s,
     dt.jonah_z = dft.jonah_z.data(); dt.bulkPi_over_Peq_max = dft.bulkPi_over_Peq_max;
   }
   is3d_laguerre la{gla.points, gla.root[1].data(), gla.weight[1].data(), gla.root[2].data(), gla.weight[2].data()};
+  if (P.operation == 0) {
+    // spacetime distributions (emissionfunction.cpp:1512-1516, 1577-1581): nothing else is written for this operation
+    is3d_spacetime_bins b; std::memset(&b, 0, sizeof(b));
+    std::string e2;
+    b.tau_min = P.par.get("tau_min", &e2); b.tau_max = P.par.get("tau_max", &e2); b.tau_bins = (int32_t)P.par.get("tau_bins", &e2);
+    b.r_min = P.par.get("r_min", &e2); b.r_max = P.par.get("r_max", &e2); b.r_bins = (int32_t)P.par.get("r_bins", &e2);
+    b.pT_weight = g.pT.cols[1].data(); b.phi_weight = g.phi.cols[1].data();
+    if (b.tau_bins <= 0 || b.r_bins <= 0) { err = "tau_bins and r_bins must be positive"; return IS3D_ERR_ARGUMENT; }
+    const int eta_pts = (P.fl.dimension == 2) ? (int)g.eta.rows : 1;
+    const size_t nt = (size_t)b.tau_bins, nr = (size_t)b.r_bins;
+    std::vector<double> h_tau(npart * nt), h_r(npart * nr), h_taur(npart * nt * nr), h_eta((size_t)npart * eta_pts), h_y((size_t)npart);
+    is3d_spacetime_result res{h_tau.data(), h_r.data(), h_taur.data(), h_eta.data(), h_y.data()};
+    is3d_stats st0; std::memset(&st0, 0, sizeof(st0));
+    const int rc0 = is3d_b200_spacetime_distributions(&P.fl, &s, &sp, &gr, &dt, &la, &b, nullptr, &res, &st0);
+    if (stats) *stats = st0;
+    if (rc0 != IS3D_OK) { err = std::string("spacetime kernel failed: ") + is3d_b200_last_error(); return rc0; }
+    std::vector<double> eta_values(eta_pts, 0.0);
+    if (P.fl.dimension == 2) for (int j = 0; j < eta_pts; j++) eta_values[j] = g.eta.at(1, j + 1);
+    else if (s.n_cells > 0) eta_values[0] = s.eta[s.n_cells - 1];          // the reference's etaValues[0] still holds the last cell's eta (:1154)
+    for (int i = 0; i < npart; i++) std::printf("dN_dy = %lf\n", h_y[i]);   // :1439-1442
+    if (dN_raw) {                                                          // [dN_tau | dN_r | dN_taur | dN_dydeta | dN_dy]
+      std::vector<double> all;
+      for (const std::vector<double> *v : {&h_tau, &h_r, &h_taur, &h_eta, &h_y}) all.insert(all.end(), v->begin(), v->end());
+      std::memcpy(dN_raw, all.data(), sizeof(double) * (size_t)std::min<int64_t>(n_raw, (int64_t)all.size()));
+    }
+    if (mcid_out) for (int i = 0; i < npart && i < n_mcid_max; i++) mcid_out[i] = P.mcid[i];
+    if (!write_spacetime_files(wd, P.mcid, b, eta_pts, eta_values, h_tau, h_r, h_taur, h_eta, &err)) return IS3D_ERR_IO;
+    return IS3D_OK;
+  }
   const size_t n_bins = (size_t)npart * g.pT.rows * g.phi.rows * g.y.rows;
   std::vector<double> dN(n_bins, 0.0);
   is3d_stats st; std::memset(&st, 0, sizeof(st));
@@ -253,6 +316,7 @@ extern "C" int is3d_b200_run_workdir(const char *workdir, double *dN_raw, int64_
   s.ux = sf.ux.data(); s.uy = sf.uy.data(); s.un = sf.un.data(); s.T = sf.T.data(); s.P = sf.P.data(); s.E = sf.E.data();
   s.pixx = sf.pixx.data(); s.pixy = sf.pixy.data(); s.pixn = sf.pixn.data(); s.piyy = sf.piyy.data(); s.piyn = sf.piyn.data();
   s.bulkPi = sf.bulkPi.data(); s.muB = sf.muB.data(); s.nB = sf.nB.data(); s.Vx = sf.Vx.data(); s.Vy = sf.Vy.data(); s.Vn = sf.Vn.data();
+  s.x = sf.x.data(); s.y = sf.y.data();
   if (P.fl.mode == 2) {
     s.pitt = sf.pitt.data(); s.pitx = sf.pitx.data(); s.pity = sf.pity.data(); s.pitn = sf.pitn.data(); s.pinn = sf.pinn.data();
     s.Wx = sf.Wx.data(); s.Wy = sf.Wy.data(); s.Lambda = sf.Lambda.data(); s.aL = sf.aL.data();

@@ -519,9 +519,19 @@ typedef struct {
   double neq_fact, dn_fact, J20_fact, N10_fact, nmod_fact;
 } feqmod_setup;
 
-int64_t cfo_smooth_feqmod(const cfo_flags *fl, const cfo_cells *c, const cfo_species *sp, const cfo_grid *g,
-                          const cfo_df_tables *tab, const cfo_laguerre *gla, double *dN, int64_t *breakdown_out)
+/* One restatement serves both feqmod routines.  spec == NULL: calculate_dN_ptdptdphidy_feqmod (:396-996), result in dN.
+ * spec != NULL: calculate_dN_dX_feqmod (:1449-2135), result in the histograms; that routine differs from the first in
+ *   - the Jonah bulk-pressure clamp uses <= / >= (:1709-1710 vs :591-592),
+ *   - eta_scale = detA whenever detA > detA_min in 2+1D, without the detA < 1 condition (:1850-1853 vs :729),
+ *   - the renormalisation NaN/Inf test is made on renorm / detA (:1887 vs :773),
+ *   - the "narrow" per-rapidity breakdown is commented out (:1927-1935 vs :813-819),
+ *   - p.dsigma = eta_weight * (pt dat + px dax + py day + pn dan) in both branches (:1948, :2001 vs :832, :883),
+ *   - its `breakdown` counter runs inside the species loop (npart times the cell count); the cell count is returned here. */
+static int64_t feqmod_core(const cfo_flags *fl, const cfo_cells *c, const cfo_species *sp, const cfo_grid *g,
+                           const cfo_df_tables *tab, const cfo_laguerre *gla, double *dN, int64_t *breakdown_out,
+                           const cfo_spacetime_spec *spec, double *dN_tau, double *dN_r, double *dN_taur, double *dN_dydeta, double *dN_dy)
 {
+  const int dX = (spec != NULL);
   if (fl->df_mode != 3 && fl->df_mode != 4) return -1;
   if (fl->include_baryon) return -2;
   const double prefactor = pow(2.0 * M_PI * hbarC, -3);
@@ -540,8 +550,13 @@ int64_t cfo_smooth_feqmod(const cfo_flags *fl, const cfo_cells *c, const cfo_spe
     double uperp = sqrt(s->ux * s->ux + s->uy * s->uy), utperp = sqrt(1.0 + s->ux * s->ux + s->uy * s->uy);
     if (DF_MODE == 4) {                                              /* :588-594 */
       double mx = tab->bulkPi_over_Peq_max;
-      if (s->bulkPi < -s->P) s->bulkPi = -(1.0 - 1.e-5) * s->P;
-      else if (s->bulkPi / s->P > mx) s->bulkPi = s->P * (mx - 1.e-5);
+      if (dX) {
+        if (s->bulkPi <= -s->P) s->bulkPi = -(1.0 - 1.e-5) * s->P;
+        else if (s->bulkPi / s->P >= mx) s->bulkPi = s->P * (mx - 1.e-5);
+      } else {
+        if (s->bulkPi < -s->P) s->bulkPi = -(1.0 - 1.e-5) * s->P;
+        else if (s->bulkPi / s->P > mx) s->bulkPi = s->P * (mx - 1.e-5);
+      }
     }
     if (df_eval(&sc, DF_MODE, s->T, s->E, s->P, s->bulkPi, &s->df)) bad = 1;
     const cfo_dfcoef *df = &s->df;
@@ -590,7 +605,7 @@ int64_t cfo_smooth_feqmod(const cfo_flags *fl, const cfo_cells *c, const cfo_spe
     }
     if (f->breaks_down) breakdown++;
     f->eta_scale = 1.0;
-    if (f->detA > detA_min && f->detA < 1.0 && fl->dimension == 2) f->eta_scale = f->detA;
+    if (f->detA > detA_min && (dX || f->detA < 1.0) && fl->dimension == 2) f->eta_scale = f->detA;
   }
   cache_free(&sc);
   if (bad) { free(cs); return -3; }
@@ -601,9 +616,13 @@ int64_t cfo_smooth_feqmod(const cfo_flags *fl, const cfo_cells *c, const cfo_spe
   for (int ipart = 0; ipart < npart; ipart++) {
     double mass = sp->mass[ipart], mass2 = mass * mass, sign = sp->sign[ipart];
     double degeneracy = sp->degeneracy[ipart], baryon = sp->baryon[ipart];
+    double *h_tau = dX ? dN_tau + (int64_t)ipart * spec->tau_bins : NULL, *h_r = dX ? dN_r + (int64_t)ipart * spec->r_bins : NULL;
+    double *h_taur = dX ? dN_taur + (int64_t)ipart * spec->tau_bins * spec->r_bins : NULL;
+    double *h_eta = dX ? dN_dydeta + (int64_t)ipart * eta_pts : NULL;
     for (int64_t icell = 0; icell < n; icell++) {
       const feqmod_setup *fs = &cs[icell]; const cell_setup *s = &fs->s; const milne_basis *b = &fs->b;
       if (s->skip) continue;
+      double dN_dy_cell = 0.0;
       const cfo_dfcoef *df = &s->df;
       double chem = baryon * s->alphaB, chem_mod = baryon * fs->alphaB_mod;
       double renorm = 1.0;
@@ -618,14 +637,16 @@ int64_t cfo_smooth_feqmod(const cfo_flags *fl, const cfo_cells *c, const cfo_spe
           renorm = n_linear / n_mod;
         } else renorm = df->z;
       }
-      if (isnan(renorm) || isinf(renorm)) continue;                      /* :773-778 */
+      if (dX ? (isnan(renorm / fs->detA) || isinf(renorm / fs->detA)) : (isnan(renorm) || isinf(renorm))) continue;   /* :773-778, :1887-1891 */
       if (fl->dimension == 3) renorm /= fs->detA;
       for (int ipT = 0; ipT < npT; ipT++) {
         double pT = g->pT[ipT];
         double mT = sqrt(mass2 + pT * pT);
         double mT_over_tau = mT / s->tau;
+        const double w_pT_phi_base = dX ? spec->pT_weight[ipT] : 0.0;
         for (int iphip = 0; iphip < nphi; iphip++) {
           double px = pT * cosphi[iphip], py = pT * sinphi[iphip];
+          const double pT_weight = w_pT_phi_base, phi_weight = g->phi_weight ? g->phi_weight[iphip] : 0.0;
           for (int iy = 0; iy < y_pts; iy++) {
             double y = (fl->dimension == 2) ? 0.0 : g->y[iy];
             double sum = 0.0;
@@ -633,13 +654,14 @@ int64_t cfo_smooth_feqmod(const cfo_flags *fl, const cfo_cells *c, const cfo_spe
               double eta = (fl->dimension == 2) ? g->eta[ieta] : s->eta;
               double eta_weight = (fl->dimension == 2) ? g->eta_weight[ieta] : 1.0;
               int narrow = 0;
-              if (fl->dimension == 3 && !fs->breaks_down) { if (fs->detA < 0.01 && fabs(y - eta) < fs->detA) narrow = 1; }
+              if (!dX && fl->dimension == 3 && !fs->breaks_down) { if (fs->detA < 0.01 && fabs(y - eta) < fs->detA) narrow = 1; }
               double pdotdsigma, f = 0.0;
               if (fs->breaks_down || narrow) {                           /* :825-877 */
                 double pt = mT * cosh(y - eta);
                 double pn = mT_over_tau * sinh(y - eta);
                 double tau2_pn = s->tau2 * pn;
-                pdotdsigma = eta_weight * (pt * s->dat + px * s->dax + py * s->day) + pn * s->dan;
+                pdotdsigma = dX ? eta_weight * (pt * s->dat + px * s->dax + py * s->day + pn * s->dan)
+                                : eta_weight * (pt * s->dat + px * s->dax + py * s->day) + pn * s->dan;
                 if (fl->outflow && pdotdsigma <= 0.0) continue;
                 double pdotu = pt * s->ut - px * s->ux - py * s->uy - tau2_pn * s->un;
                 double pimunu_pmu_pnu = s->pitt * pt * pt + s->pixx * px * px + s->piyy * py * py + s->pinn * tau2_pn * tau2_pn
@@ -667,7 +689,8 @@ int64_t cfo_smooth_feqmod(const cfo_flags *fl, const cfo_cells *c, const cfo_spe
                 double pt = mT * cosh(y - fs->eta_scale * eta);
                 double pn = mT_over_tau * sinh(y - fs->eta_scale * eta);
                 double tau2_pn = s->tau2 * pn;
-                pdotdsigma = eta_weight * (pt * s->dat + px * s->dax + py * s->day) + pn * s->dan;
+                pdotdsigma = dX ? eta_weight * (pt * s->dat + px * s->dax + py * s->day + pn * s->dan)
+                                : eta_weight * (pt * s->dat + px * s->dax + py * s->day) + pn * s->dan;
                 if (fl->outflow && pdotdsigma <= 0.0) continue;
                 double pLRF[3] = {-b->Xt * pt + b->Xx * px + b->Xy * py + b->Xn * tau2_pn, b->Yx * px + b->Yy * py, -b->Zt * pt + b->Zn * tau2_pn};
                 double pmod[3], pmod_prev[3], pprev[3], dp3[3], dpmod[3];
@@ -685,17 +708,37 @@ int64_t cfo_smooth_feqmod(const cfo_flags *fl, const cfo_cells *c, const cfo_spe
                 f = fabs(renorm) / (exp(E_mod / fs->T_mod - chem_mod) + sign);
               }
               sum += (pdotdsigma * f);
+              if (dX) h_eta[ieta] += (pT_weight * phi_weight * prefactor * degeneracy * pdotdsigma * f / eta_weight);
             }
+            if (dX) { dN_dy_cell += (pT_weight * phi_weight * prefactor * degeneracy * sum); continue; }
             int64_t iS3D = (int64_t)ipart + (int64_t)npart * ((int64_t)ipT + (int64_t)npT * ((int64_t)iphip + (int64_t)nphi * (int64_t)iy));
             dN[iS3D] += (prefactor * degeneracy * sum);
           }
         }
+      }
+      if (dX) {
+        dN_dy[ipart] += dN_dy_cell;
+        spacetime_bin(spec, s->tau, spec->x[icell], spec->y[icell], dN_dy_cell, h_tau, h_r, h_taur);
       }
     }
   }
   free(cs); free(cosphi); free(sinphi);
   if (breakdown_out) *breakdown_out = breakdown;
   return skipped;
+}
+
+int64_t cfo_smooth_feqmod(const cfo_flags *fl, const cfo_cells *c, const cfo_species *sp, const cfo_grid *g,
+                          const cfo_df_tables *tab, const cfo_laguerre *gla, double *dN, int64_t *breakdown_out)
+{
+  return feqmod_core(fl, c, sp, g, tab, gla, dN, breakdown_out, NULL, NULL, NULL, NULL, NULL, NULL);
+}
+
+int64_t cfo_spacetime_feqmod(const cfo_flags *fl, const cfo_cells *c, const cfo_species *sp, const cfo_grid *g,
+                             const cfo_df_tables *tab, const cfo_laguerre *gla, const cfo_spacetime_spec *spec,
+                             double *dN_tau, double *dN_r, double *dN_taur, double *dN_dydeta, double *dN_dy, int64_t *breakdown_out)
+{
+  if (!spec) return -1;
+  return feqmod_core(fl, c, sp, g, tab, gla, NULL, breakdown_out, spec, dN_tau, dN_r, dN_taur, dN_dydeta, dN_dy);
 }
 
 /* ---------------------------------------------------------------- a3: anisotropic PL-matching kernel, :2140-2393 */

@@ -108,6 +108,12 @@ int64_t cfo_spacetime_vh(const cfo_flags *fl, const cfo_cells *c, const cfo_spec
                          const cfo_df_tables *tab, const cfo_spacetime_spec *spec,
                          double *dN_tau, double *dN_r, double *dN_taur, double *dN_dydeta, double *dN_dy);
 
+/* EmissionFunctionArray::calculate_dN_dX_feqmod, :1449-2135 (df_mode 3,4); *breakdown gets the number of cells that break down
+ * (the reference's printed counter is n_species times that, it is incremented inside the species loop). */
+int64_t cfo_spacetime_feqmod(const cfo_flags *fl, const cfo_cells *c, const cfo_species *sp, const cfo_grid *g,
+                             const cfo_df_tables *tab, const cfo_laguerre *gla, const cfo_spacetime_spec *spec,
+                             double *dN_tau, double *dN_r, double *dN_taur, double *dN_dydeta, double *dN_dy, int64_t *breakdown);
+
 /* VAH helpers: aL_fit / R200 (arsenal.cpp:999-1066) and the (Lambda, aL) bilinear lookup of
  * src/cuda/deltafReader.cu:192-277 */
 double cfo_aL_fit(double pl_over_peq);

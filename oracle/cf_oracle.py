@@ -68,6 +68,7 @@ def lib():
         L.cfo_smooth_feqmod.restype = C.c_int64
         L.cfo_smooth_vah.restype = C.c_int64
         L.cfo_spacetime_vh.restype = C.c_int64
+        L.cfo_spacetime_feqmod.restype = C.c_int64
         L.cfo_jonah_tables.restype = C.c_double
         L.cfo_aL_fit.restype = C.c_double; L.cfo_aL_fit.argtypes = [C.c_double]
         L.cfo_R200.restype = C.c_double; L.cfo_R200.argtypes = [C.c_double]
@@ -202,7 +203,11 @@ def spacetime(flags, cells, species, grid, tables, bins, laguerre=None):
         rc = lib().cfo_spacetime_vh(C.byref(fl), C.byref(c), C.byref(sp), C.byref(g), C.byref(t), C.byref(spec),
                                     _p(out["dN_tau"]), _p(out["dN_r"]), _p(out["dN_taur"]), _p(out["dN_dydeta"]), _p(out["dN_dy"]))
     else:
-        raise NotImplementedError("spacetime oracle: df_mode %d" % flags["df_mode"])
+        la = _laguerre(keep, laguerre); bd = C.c_int64(0)
+        rc = lib().cfo_spacetime_feqmod(C.byref(fl), C.byref(c), C.byref(sp), C.byref(g), C.byref(t), C.byref(la), C.byref(spec),
+                                        _p(out["dN_tau"]), _p(out["dN_r"]), _p(out["dN_taur"]), _p(out["dN_dydeta"]), _p(out["dN_dy"]),
+                                        C.byref(bd))
+        out["breakdown"] = int(bd.value)
     if rc < 0:
         raise RuntimeError("cf_oracle error %d" % rc)
     return out, int(rc)

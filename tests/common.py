@@ -123,3 +123,39 @@ def compare(got, ref, tol=REL_TOL, conditioning=None):
     return dict(max_rel=float(rel.max()) if rel.size else 0.0, median_rel=float(np.median(rel)) if rel.size else 0.0,
                 zeros_match=bool(np.all(got[~nz] == 0)), worst_bin=int(idx), worst_ref=float(ref[idx]) if rel.size else 0.0,
                 ok=bool((rel.size == 0 or rel.max() <= tol) and np.all(got[~nz] == 0)))
+
+
+# ------------------------------------------------------------------------------------------ operation = 0 golden vectors
+def spacetime_names():
+    return sorted(os.path.basename(p)[len("spacetime_"):-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "spacetime_*.npz")))
+
+
+def load_spacetime(name):
+    z = np.load(os.path.join(GOLDEN_DIR, "spacetime_%s.npz" % name))
+    out = {k: z[k] for k in z.files}
+    out["recipe"] = json.loads(str(z["recipe"]))
+    out["file_text"] = json.loads(str(z["file_text"]))
+    return out
+
+
+def spacetime_problem(recipe, fx):
+    """(flags, cells incl. x, y, species, grid, df tables, laguerre, bins, surface columns) of a spacetime golden vector"""
+    from is3d_b200 import synthetic, tables
+    cols = synthetic.surface_vh(recipe["n_cells"], recipe["seed"], **recipe["kwargs"])
+    cells = synthetic.columns_to_cells(cols, 1)
+    prm = recipe["params"]
+    sp = tables.species(fx, prm["hrg_eos"], "chosen_pikp"); g = tables.grid(fx); tab = tables.df_tables(fx, prm["hrg_eos"])
+    gla = tables.laguerre(fx)
+    if prm["df_mode"] == 4:
+        tab.update(jonah_tables(cells, fx, prm["hrg_eos"], gla))
+    fl = tables.flags(df_mode=prm["df_mode"], dimension=prm["dimension"])
+    return fl, cells, sp, g, tab, gla, recipe["bins"], cols
+
+
+def spacetime_close(got, gold, rel=2e-6):
+    """7-significant-digit text precision of the reference files: compare against each histogram's largest entry"""
+    for k in ("dN_tau", "dN_r", "dN_taur", "dN_dydeta"):
+        a = np.asarray(got[k], dtype=np.float64).reshape(gold[k].shape)
+        scale = np.abs(gold[k]).max()
+        assert np.abs(a - gold[k]).max() <= rel * scale, k
+    assert np.abs(np.asarray(got["dN_dy"]) - gold["dN_dy_printed"]).max() < 1e-6

@@ -27,7 +27,7 @@ def test_header_symbols_are_exported():
 def test_struct_sizes_match_header():
     # int32 x9 + 4 pad + 2 doubles; int64 + 37 pointers; ...
     assert ctypes.sizeof(api.Flags) == 56
-    assert ctypes.sizeof(api.Surface) == 8 + 8 * 37
+    assert ctypes.sizeof(api.Surface) == 8 + 8 * 39
     assert ctypes.sizeof(api.Species) == 8 + 8 * 4
     assert ctypes.sizeof(api.Grid) == 16 + 8 * 5
     assert ctypes.sizeof(api.Options) == 4 + 4 + 8 + 4 + 4 + 16
