@@ -46,3 +46,32 @@ def smooth_spectra_sharded(flags, cells, species, grid, df_tables=None, laguerre
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
             dN = t.numpy()
     return dN, stats
+
+
+SPACETIME_KEYS = ("dN_tau", "dN_r", "dN_taur", "dN_dydeta", "dN_dy")
+
+
+def spacetime_distributions_sharded(flags, cells, species, grid, df_tables, laguerre, bins, memory="host", kernel=None,
+                                    group=None, already_sharded=False, **kw):
+    """operation = 0 on the local shard + ONE all-reduce of the concatenated histograms (they are sums over cells, so the
+    shards simply add).  Returns (dict of reduced raw sums, local stats)."""
+    import torch
+    import torch.distributed as dist
+    if kernel is None:
+        from . import api
+        kernel = api.spacetime_distributions
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    local = cells if already_sharded else shard_cells(cells, rank, world)
+    res, stats = kernel(flags, local, species, grid, df_tables, laguerre, bins, memory=memory, **kw)
+    if world > 1:
+        shapes = [np.asarray(res[k]).shape for k in SPACETIME_KEYS]
+        flat = torch.from_numpy(np.concatenate([np.asarray(res[k], dtype=np.float64).ravel() for k in SPACETIME_KEYS]))
+        if memory == "device":
+            flat = flat.cuda()
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat = flat.cpu().numpy()
+        off = 0
+        for k, shp in zip(SPACETIME_KEYS, shapes):
+            n = int(np.prod(shp)); res[k] = flat[off:off + n].reshape(shp); off += n
+    return res, stats

@@ -55,3 +55,36 @@ def test_two_rank_gloo_matches_single(tmp_path, name):
     # summation order changes with the number of shards: bounded by a few ulp because all terms are >= 0
     assert np.max(np.abs(d0[nz] - gold["dN"][nz]) / gold["dN"][nz]) < 1e-13
     assert np.all(d0[~nz] == 0)
+
+
+# ------------------------------------------------------------------------------------------ operation = 0 (spacetime distributions)
+def _oracle_spacetime(flags, cells, species, grid, df_tables, laguerre, bins, memory="host", **kw):
+    from oracle import cf_oracle as cfo
+    out, skipped = cfo.spacetime(flags, cells, species, grid, df_tables, bins, laguerre)
+    bd = out.pop("breakdown", 0)
+    return out, dict(cells_skipped_udsigma=skipped, cells_feqmod_breakdown=bd)
+
+
+def _worker_spacetime(rank, world, port, name, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from common import load_spacetime, spacetime_problem
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fx = tables.load_fixture()
+    gold = load_spacetime(name)
+    fl, cells, sp, g, tab, gla, bins, _ = spacetime_problem(gold["recipe"], fx)
+    res, st = distributed.spacetime_distributions_sharded(fl, cells, sp, g, tab, gla, bins, kernel=_oracle_spacetime)
+    np.savez(os.path.join(out_dir, "st_%d.npz" % rank), **res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_spacetime(tmp_path):
+    from common import load_spacetime, spacetime_close
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker_spacetime, args=(2, port, "dx3_df4", str(tmp_path)), nprocs=2, join=True)
+    r0 = np.load(tmp_path / "st_0.npz"); r1 = np.load(tmp_path / "st_1.npz")
+    for k in distributed.SPACETIME_KEYS:
+        assert np.array_equal(r0[k], r1[k])
+    spacetime_close({k: r0[k] for k in r0.files}, load_spacetime("dx3_df4"))
