@@ -22,6 +22,10 @@ namespace is3d {
 
 // Bose/Fermi factor 1 / (e^x + Theta) from a = e^{-x}
 __device__ __forceinline__ double occupation(double a, double sign) { return a * rcp_fast(fma(sign, a, 1.0)); }
+// The same plus 1 - Theta f_eq, which equals 1 / (1 + Theta e^{-x}) exactly: the reciprocal itself (one DFMA less, and more
+// accurate than the reference's 1 - sign * feq where that cancels)
+__device__ __forceinline__ double occupation_bar(double a, double sign, double &feqbar)
+{ feqbar = rcp_fast(fma(sign, a, 1.0)); return a * feqbar; }
 
 // f_eq (1 + df) of the linear-df models; x = u.p/T, s = partial delta-f polynomial (see cf_prepare.cu)
 template <int MODEL>
@@ -44,7 +48,7 @@ __device__ __forceinline__ double distribution(double x, double s, double K2, do
 // e^{-x[i]} for a group of N arguments, staged so that the N polynomial chains interleave and the (rare) sub-normal branch
 // is taken once per group
 // Dead members (alive[i] false: x beyond the overflow threshold) are NOT sanitised: their results are garbage and must be
-// discarded by the caller (the accumulate is predicated off through a -0.0 weight), which keeps selects off the chain.
+// discarded by the caller (accumulate_alive() is predicated on alive[i]), which keeps selects off the chain.
 template <int N>
 __device__ __forceinline__ void exp_neg_group(const double (&x)[N], const bool (&alive)[N], double (&a)[N])
 {
@@ -56,7 +60,7 @@ __device__ __forceinline__ void exp_neg_group(const double (&x)[N], const bool (
   for (int i = 0; i < N; i++) a[i] = exp_neg_fast(p[i], n[i]);
   if (__builtin_expect(rare, 0)) {
 #pragma unroll
-    for (int i = 0; i < N; i++) if (alive[i] && exp_neg_is_rare(n[i])) a[i] = exp_neg_rare(p[i], n[i]);
+    for (int i = 0; i < N; i++) if (alive[i] && exp_neg_is_rare(n[i])) a[i] = exp_finite(x[i]) ? exp_neg_rare(p[i], n[i]) : 0.0;
   }
 }
 
@@ -68,15 +72,15 @@ __device__ __forceinline__ double distribution_from_a(double a, double x, double
   double dfs;
   if (MODEL == M_LIN14) dfs = fma(K2 * x, x, s);
   else dfs = fma(s, rcp_fast(x), K2 * x);
-  const double feq = occupation(a, sign);
-  const double feqbar = fma(-sign, feq, 1.0);
+  double feqbar;
+  const double feq = occupation_bar(a, sign, feqbar);
   double df = (MODEL == M_JONAHLIN) ? fma(feqbar, dfs, K3) : feqbar * dfs;
   df = clamp_unit(df, reg_thr);
   return fma(feq, df, feq);
 }
 
 // Same as distribution() for a group of N evaluations, staged so that the N dependency chains can be interleaved and the
-// (rare) sub-normal branch is taken once per group.  pds[i] == 0 marks dead members.
+// (rare) sub-normal branch is taken once per group.  Results of dead members (alive[i] false) are garbage.
 template <int MODEL, int N>
 __device__ __forceinline__ void distribution_group(const double (&x)[N], const bool (&alive)[N], const double (&s)[N], double K2, double K3,
                                                    double sign, int reg_thr, double (&f)[N])
@@ -95,13 +99,13 @@ __device__ __forceinline__ void distribution_group(const double (&x)[N], const b
   for (int i = 0; i < N; i++) a[i] = exp_neg_fast(p[i], n[i]);
   if (__builtin_expect(rare, 0)) {
 #pragma unroll
-    for (int i = 0; i < N; i++) if (alive[i] && exp_neg_is_rare(n[i])) a[i] = exp_neg_rare(p[i], n[i]);
+    for (int i = 0; i < N; i++) if (alive[i] && exp_neg_is_rare(n[i])) a[i] = exp_finite(x[i]) ? exp_neg_rare(p[i], n[i]) : 0.0;
   }
 #pragma unroll
   for (int i = 0; i < N; i++) {
-    const double feq = occupation(a[i], sign);
+    double feqbar;
+    const double feq = occupation_bar(a[i], sign, feqbar);
     if (MODEL == M_IDEAL) { f[i] = feq; continue; }
-    const double feqbar = fma(-sign, feq, 1.0);
     double df = (MODEL == M_JONAHLIN) ? fma(feqbar, dfs[i], K3) : feqbar * dfs[i];
     df = clamp_unit(df, reg_thr);
     f[i] = fma(feq, df, feq);
@@ -142,6 +146,7 @@ cf_kernel(const HotParams hp)
   const double mT = sqrt(mT2);
   const int reg_thr = hp.regulate_thr;
   const long long thr = hp.outflow_thr;
+  const int thr_hi = (int)(thr >> 32);                       // grouped paths test the high word of p.dsigma only
   const double *renorm = (MODEL == M_FEQMOD && hp.renorm) ? hp.renorm + (int64_t)ipart * L.n_cells_pad : nullptr;
 
   // ---- cell tiles of this chunk: balanced contiguous split of [0, n_tiles), or the caller's table ((tau, r) bins)
@@ -154,6 +159,7 @@ cf_kernel(const HotParams hp)
   const double *Sg = hp.S;
   const uint32_t stage_bytes = (uint32_t)stage_doubles * 8u;
 
+  exp_table_init();
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
     mbar_fence_init();
@@ -241,14 +247,14 @@ cf_kernel(const HotParams hp)
               const double p1 = e1 + g1[k], p2 = e2 + g2[k], p3 = e3 + g3[k];
               double E2 = fma(p1, p1, g0[k]); E2 = fma(p2, p2, E2); E2 = fma(p3, p3, E2);
               xv[k] = sqrt_fast(E2);
-              lv[k] = exp_finite(xv[k]);
+              lv[k] = exp_alive_hi(xv[k]);
               any |= lv[k];
-              pv[k] = lv[k] ? fma(w, pd[k], cpm) : -0.0;
+              pv[k] = fma(w, pd[k], cpm);
             }
             if (any) {
               exp_neg_group<NPT>(xv, lv, av);
 #pragma unroll
-              for (int k = 0; k < NPT; k++) accumulate_outflow(accj[k], pv[k], rn * occupation(av[k], sign), thr);
+              for (int k = 0; k < NPT; k++) accumulate_alive(accj[k], pv[k], rn * occupation(av[k], sign), thr_hi, xv[k]);
             }
           }
         } else if (MODEL == M_VAH) {
@@ -279,9 +285,9 @@ cf_kernel(const HotParams hp)
             for (int k = 0; k < NPT; k++) {
               const double u = a - q[k];
               xv[k] = sqrt_fast(fma(u, u, hz));
-              lv[k] = exp_finite(xv[k]);
+              lv[k] = exp_alive_hi(xv[k]);
               any |= lv[k];
-              pv[k] = lv[k] ? fma(w, pd[k], cpm) : -0.0;
+              pv[k] = fma(w, pd[k], cpm);
               double s = h0 + g0[k];
               s = fma(g2[k], h2, s);
               s = fma(-g1[k], h1, s);
@@ -292,10 +298,10 @@ cf_kernel(const HotParams hp)
               exp_neg_group<NPT>(xv, lv, av);
 #pragma unroll
               for (int k = 0; k < NPT; k++) {
-                const double fa = occupation(av[k], sign);
-                const double fabar = fma(-sign, fa, 1.0);
+                double fabar;
+                const double fa = occupation_bar(av[k], sign, fabar);
                 const double df = clamp_unit(fabar * sv[k], reg_thr);
-                accumulate_outflow(accj[k], pv[k], fma(fa, df, fa), thr);
+                accumulate_alive(accj[k], pv[k], fma(fa, df, fa), thr_hi, xv[k]);
               }
             }
           }
@@ -318,7 +324,7 @@ cf_kernel(const HotParams hp)
             // e^{-x} = e^{-mT Ax} e^{+pT Bx}: one exponential per slot and one per phi point instead of one per evaluation
             double xs[NPT]; bool alive[NPT]; bool any = false;
 #pragma unroll
-            for (int k = 0; k < NPT; k++) { xs[k] = a - q[k]; alive[k] = exp_finite(xs[k]); any |= alive[k]; }
+            for (int k = 0; k < NPT; k++) { xs[k] = a - q[k]; alive[k] = exp_alive_hi(xs[k]); any |= alive[k]; }
             if (any) {
               double pe; int ne;
               exp_neg_poly(a, pe, ne);
@@ -332,33 +338,34 @@ cf_kernel(const HotParams hp)
               }
               if (__builtin_expect(rare, 0)) {
 #pragma unroll
-                for (int k = 0; k < NPT; k++) if (alive[k] && exp_neg_is_rare(ne + fm[k])) av[k] = exp_neg_rare(pe * fq[k], ne + fm[k]);
+                for (int k = 0; k < NPT; k++)
+                  if (alive[k] && exp_neg_is_rare(ne + fm[k])) av[k] = exp_finite(xs[k]) ? exp_neg_rare(pe * fq[k], ne + fm[k]) : 0.0;
               }
 #pragma unroll
               for (int k = 0; k < NPT; k++) {
-                const double pds = alive[k] ? fma(w, pd[k], cpm) : -0.0;
+                const double pds = fma(w, pd[k], cpm);
                 double s = h0 + g0[k];
                 s = fma(g2[k], h2, s);
                 s = fma(-g1[k], h1, s);
-                accumulate_outflow(accj[k], pds, distribution_from_a<MODEL>(av[k], xs[k], s, K2, K3, sign, reg_thr), thr);
+                accumulate_alive(accj[k], pds, distribution_from_a<MODEL>(av[k], xs[k], s, K2, K3, sign, reg_thr), thr_hi, xs[k]);
               }
             }
           } else {
             double xs[NPT]; bool alive[NPT]; bool any = false;
 #pragma unroll
-            for (int k = 0; k < NPT; k++) { xs[k] = a - q[k]; alive[k] = exp_finite(xs[k]); any |= alive[k]; }
+            for (int k = 0; k < NPT; k++) { xs[k] = a - q[k]; alive[k] = exp_alive_hi(xs[k]); any |= alive[k]; }
             if (any) {
               double sv[NPT], pv[NPT], fv[NPT];
 #pragma unroll
               for (int k = 0; k < NPT; k++) {
-                pv[k] = alive[k] ? fma(w, pd[k], cpm) : -0.0;                  // -0.0 never passes the p.dsigma test
+                pv[k] = fma(w, pd[k], cpm);
                 double s = h0 + g0[k];
                 s = fma(g2[k], h2, s);
                 sv[k] = fma(-g1[k], h1, s);
               }
               distribution_group<MODEL, NPT>(xs, alive, sv, K2, K3, sign, reg_thr, fv);
 #pragma unroll
-              for (int k = 0; k < NPT; k++) accumulate_outflow(accj[k], pv[k], fv[k], thr);
+              for (int k = 0; k < NPT; k++) accumulate_alive(accj[k], pv[k], fv[k], thr_hi, xs[k]);
             }
           }
         }
@@ -374,21 +381,21 @@ cf_kernel(const HotParams hp)
 #pragma unroll
         for (int k = 0; k < NPT; k++) {
           xA[k] = aA - q[k]; xB[k] = aB - q[k];
-          lA[k] = exp_finite(xA[k]); lB[k] = exp_finite(xB[k]); any |= lA[k] | lB[k];
+          lA[k] = exp_alive_hi(xA[k]); lB[k] = exp_alive_hi(xB[k]); any |= lA[k] | lB[k];
         }
         if (any) {
           double xv[2 * NPT], sv[2 * NPT], pv[2 * NPT], fv[2 * NPT]; bool lv[2 * NPT];
 #pragma unroll
           for (int k = 0; k < NPT; k++) {
             xv[k] = xA[k]; xv[NPT + k] = xB[k]; lv[k] = lA[k]; lv[NPT + k] = lB[k];
-            pv[k] = lA[k] ? fma(wA, pd[k], cA) : -0.0; pv[NPT + k] = lB[k] ? fma(wB, pd[k], cB) : -0.0;
+            pv[k] = fma(wA, pd[k], cA); pv[NPT + k] = fma(wB, pd[k], cB);
             double s0 = h0A + g0[k], s1 = h0B + g0[k];
             s0 = fma(g2[k], h2A, s0); s1 = fma(g2[k], h2B, s1);
             sv[k] = fma(-g1[k], h1A, s0); sv[NPT + k] = fma(-g1[k], h1B, s1);
           }
           distribution_group<MODEL, 2 * NPT>(xv, lv, sv, K2, K3, sign, reg_thr, fv);
 #pragma unroll
-          for (int k = 0; k < 2 * NPT; k++) accumulate_outflow(accj[k], pv[k], fv[k], thr);
+          for (int k = 0; k < 2 * NPT; k++) accumulate_alive(accj[k], pv[k], fv[k], thr_hi, xv[k]);
         }
       };
       // SB == 4 (linear models, 3+1D): like SB == 1, but the aliveness test of slot j + 1 is issued before slot j is
@@ -397,7 +404,7 @@ cf_kernel(const HotParams hp)
         const double a = mT * Ys[(c * nst + j) * RY];
         any = false;
 #pragma unroll
-        for (int k = 0; k < NPT; k++) { x[k] = a - q[k]; l[k] = exp_finite(x[k]); any |= l[k]; }
+        for (int k = 0; k < NPT; k++) { x[k] = a - q[k]; l[k] = exp_alive_hi(x[k]); any |= l[k]; }
       };
       auto eval_probed = [&](int j, const double (&x)[NPT], const bool (&l)[NPT], double *accj) {
         const double2 *yr = reinterpret_cast<const double2 *>(Ys + (c * nst + j) * RY);
@@ -406,14 +413,14 @@ cf_kernel(const HotParams hp)
         double sv[NPT], pv[NPT], fv[NPT];
 #pragma unroll
         for (int k = 0; k < NPT; k++) {
-          pv[k] = l[k] ? fma(w, pd[k], cpm) : -0.0;
+          pv[k] = fma(w, pd[k], cpm);
           double s = h0 + g0[k];
           s = fma(g2[k], h2, s);
           sv[k] = fma(-g1[k], h1, s);
         }
         distribution_group<MODEL, NPT>(x, l, sv, K2, K3, sign, reg_thr, fv);
 #pragma unroll
-        for (int k = 0; k < NPT; k++) accumulate_outflow(accj[k], pv[k], fv[k], thr);
+        for (int k = 0; k < NPT; k++) accumulate_alive(accj[k], pv[k], fv[k], thr_hi, x[k]);
       };
       if (DIM2) {
 #pragma unroll 2
@@ -559,7 +566,7 @@ cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, i
 // Variants >= 8 are compiled for the 14-moment model only (tuning sweep) and fall back to variant 0 elsewhere.
 struct Shape { int nyt, npt, ct, minb, sb; };
 static const Shape kShapes3D[] = {
-  {7, 1, 16, 6, 0}, {7, 3, 16, 3, 0}, {7, 2, 16, 4, 0}, {7, 4, 16, 3, 0}, {7, 2, 16, 5, 0}, {3, 6, 16, 3, 0}, {7, 6, 16, 2, 0}, {7, 3, 16, 4, 0},
+  {7, 1, 16, 6, 0}, {7, 3, 16, 3, 0}, {7, 3, 16, 5, 4}, {7, 4, 16, 3, 4}, {7, 2, 16, 6, 4}, {3, 6, 16, 3, 0}, {7, 6, 16, 2, 4}, {7, 3, 16, 4, 0},
   {7, 3, 16, 4, 3}, {7, 3, 16, 3, 4}, {7, 3, 16, 3, 3}, {7, 3, 16, 4, 1}, {7, 3, 16, 3, 1}, {7, 4, 16, 4, 1}, {7, 2, 16, 6, 1}, {7, 3, 16, 4, 4}};
 static const Shape kShapes2D[] = {
   {1, 3, 1, 4, 0}, {1, 4, 1, 4, 0}, {1, 6, 1, 3, 0}, {1, 8, 1, 3, 0}, {1, 2, 1, 5, 0}, {1, 12, 1, 2, 0}, {1, 4, 1, 3, 0}, {1, 1, 1, 6, 0},
@@ -623,11 +630,11 @@ static cudaError_t launch_model(const HotParams &hp, int variant, cudaStream_t s
   }
   switch (variant) {
     case 1: return launch_one<MODEL, 7, 3, false, 3, 0>(hp, st, smem_out);
-    case 2: return launch_one<MODEL, 7, 2, false, 4, 0>(hp, st, smem_out);
-    case 3: return launch_one<MODEL, 7, 4, false, 3, 0>(hp, st, smem_out);
-    case 4: return launch_one<MODEL, 7, 2, false, 5, 0>(hp, st, smem_out);
+    case 2: return launch_one<MODEL, 7, 3, false, 5, 4>(hp, st, smem_out);
+    case 3: return launch_one<MODEL, 7, 4, false, 3, 4>(hp, st, smem_out);
+    case 4: return launch_one<MODEL, 7, 2, false, 6, 4>(hp, st, smem_out);
     case 5: return launch_one<MODEL, 3, 6, false, 3, 0>(hp, st, smem_out);
-    case 6: return launch_one<MODEL, 7, 6, false, 2, 0>(hp, st, smem_out);
+    case 6: return launch_one<MODEL, 7, 6, false, 2, 4>(hp, st, smem_out);
     case 7: return launch_one<MODEL, 7, 3, false, 4, 0>(hp, st, smem_out);
     default: break;
   }
