@@ -480,6 +480,7 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   hp.renorm = (feqmod && fl->df_mode == 3) ? g_ws.extra.as<double>() : nullptr;
   hp.n_chunks = n_chunks; hp.n_groupblocks = n_groupblocks; hp.n_warps = n_warps;
   hp.regulate_thr = fl->regulate_deltaf ? 0x3ff00000 : 0x7ff80000;
+  hp.one_hi = 0x3ff00000;
   hp.outflow_thr = (fl->outflow && !vah) ? 0LL : (long long)0x8000000000000000ULL;   // the anisotropic kernel has no Theta(p.dsigma)
   const double hbarC = 0.197327053;
   hp.prefactor = vah ? 1.0 / (8.0 * (M_PI * M_PI * M_PI)) / hbarC / hbarC / hbarC      // smooth_kernels.cpp:2146

@@ -72,6 +72,7 @@ struct HotParams {
   long long outflow_thr;                           // bit pattern threshold of the p.dsigma > 0 test
   double prefactor;
   int regulate_thr;                                // high-word threshold of |df| >= 1, see clamp_unit()
+  int one_hi;                                      // 0x3ff00000 (high word of 1.0) as a run-time value, see clamp_unit()
   // operation = 0 (spacetime distributions): momentum-integrated epilogue instead of the spectra bins
   int integ_mode;                                  // 0 spectra; 1 sum over (slot, phi, pT) per chunk; 2 per slot, sum over (phi, pT)
   int integ_sl;                                    // species slots per block: (block lanes - 1) / n_pT + 2

@@ -26,10 +26,13 @@ __device__ __forceinline__ double occupation(double a, double sign) { return a *
 // accurate than the reference's 1 - sign * feq where that cancels)
 __device__ __forceinline__ double occupation_bar(double a, double sign, double &feqbar)
 { feqbar = rcp_fast(fma(sign, a, 1.0)); return a * feqbar; }
+// dilute form, a < 2^-18: 1 / (1 + Theta a) = 1 - Theta a + a^2 - ... truncated after a^2 (|error| < a^3 < 5.2e-17)
+__device__ __forceinline__ double occupation_bar_dilute(double a, double sign, double &feqbar)
+{ feqbar = fma(a, a, fma(-sign, a, 1.0)); return a * feqbar; }
 
 // f_eq (1 + df) of the linear-df models; x = u.p/T, s = partial delta-f polynomial (see cf_prepare.cu)
 template <int MODEL>
-__device__ __forceinline__ double distribution(double x, double s, double K2, double K3, double sign, int reg_thr)
+__device__ __forceinline__ double distribution(double x, double s, double K2, double K3, double sign, int reg_thr, int one_hi)
 {
   if (MODEL == M_IDEAL) return occupation(exp_neg(x), sign);      // df = 0: f = f_eq (1 + 0)
   double dfs;
@@ -38,77 +41,81 @@ __device__ __forceinline__ double distribution(double x, double s, double K2, do
   const double feq = occupation(exp_neg(x), sign);
   const double feqbar = fma(-sign, feq, 1.0);
   double df = (MODEL == M_JONAHLIN) ? fma(feqbar, dfs, K3) : feqbar * dfs;
-  df = clamp_unit(df, reg_thr);                                // regulate_deltaf
+  df = clamp_unit(df, reg_thr, one_hi);                                // regulate_deltaf
   return fma(feq, df, feq);
 }
 
 // SB: evaluations are grouped SB slots x NPT phi points per divergent region (0: one region per evaluation).  Grouping
 // lets the scheduler interleave the independent exp / reciprocal chains of the group (ILP); the cost is that a group is
-// evaluated as soon as one of its members is alive.
-// e^{-x[i]} for a group of N arguments, staged so that the N polynomial chains interleave and the (rare) sub-normal branch
-// is taken once per group
-// Dead members (alive[i] false: x beyond the overflow threshold) are NOT sanitised: their results are garbage and must be
-// discarded by the caller (accumulate_alive() is predicated on alive[i]), which keeps selects off the chain.
+// evaluated as soon as one of its members is alive (see group_flags() in cf_device.cuh for how dead members end up as 0).
+// e^{-x[i]} for a group of N arguments, staged so that the N polynomial chains interleave and the slow branch (sub-normal
+// results, dead members) is taken once per group
 template <int N>
-__device__ __forceinline__ void exp_neg_group(const double (&x)[N], const bool (&alive)[N], double (&a)[N])
+__device__ __forceinline__ void exp_neg_group(const double (&x)[N], bool maybe_rare, double (&a)[N])
 {
   double p[N]; int n[N];
-  bool rare = false;
 #pragma unroll
-  for (int i = 0; i < N; i++) { exp_neg_poly(x[i], p[i], n[i]); rare |= alive[i] && exp_neg_is_rare(n[i]); }
+  for (int i = 0; i < N; i++) exp_neg_poly(x[i], p[i], n[i]);
+  if (__builtin_expect(maybe_rare, 0)) {              // both sides define a[]: no register shuffling on the fast side
 #pragma unroll
-  for (int i = 0; i < N; i++) a[i] = exp_neg_fast(p[i], n[i]);
-  if (__builtin_expect(rare, 0)) {
+    for (int i = 0; i < N; i++) a[i] = exp_neg_slow(x[i], p[i], n[i]);
+  } else {
 #pragma unroll
-    for (int i = 0; i < N; i++) if (alive[i] && exp_neg_is_rare(n[i])) a[i] = exp_finite(x[i]) ? exp_neg_rare(p[i], n[i]) : 0.0;
+    for (int i = 0; i < N; i++) a[i] = exp_neg_fast(p[i], n[i]);
   }
 }
 
 // f_eq (1 + df) from a = e^{-x} (already evaluated) and the delta-f polynomial
 template <int MODEL>
-__device__ __forceinline__ double distribution_from_a(double a, double x, double s, double K2, double K3, double sign, int reg_thr)
+__device__ __forceinline__ double distribution_from_a(double a, double x, double s, double K2, double K3, double sign, int reg_thr, int one_hi,
+                                                      bool dilute)
 {
-  if (MODEL == M_IDEAL) return occupation(a, sign);
+  double feqbar, feq;
+  if (dilute) feq = occupation_bar_dilute(a, sign, feqbar);
+  else feq = occupation_bar(a, sign, feqbar);
+  if (MODEL == M_IDEAL) return feq;
   double dfs;
   if (MODEL == M_LIN14) dfs = fma(K2 * x, x, s);
   else dfs = fma(s, rcp_fast(x), K2 * x);
-  double feqbar;
-  const double feq = occupation_bar(a, sign, feqbar);
   double df = (MODEL == M_JONAHLIN) ? fma(feqbar, dfs, K3) : feqbar * dfs;
-  df = clamp_unit(df, reg_thr);
+  df = clamp_unit(df, reg_thr, one_hi);
   return fma(feq, df, feq);
 }
 
-// Same as distribution() for a group of N evaluations, staged so that the N dependency chains can be interleaved and the
-// (rare) sub-normal branch is taken once per group.  Results of dead members (alive[i] false) are garbage.
+// Same as distribution() for a group of N evaluations, staged so that the N dependency chains can be interleaved
 template <int MODEL, int N>
-__device__ __forceinline__ void distribution_group(const double (&x)[N], const bool (&alive)[N], const double (&s)[N], double K2, double K3,
-                                                   double sign, int reg_thr, double (&f)[N])
+__device__ __forceinline__ void distribution_group(const double (&x)[N], bool maybe_rare, bool all_dilute, const double (&s)[N], double K2, double K3,
+                                                   double sign, int reg_thr, int one_hi, double (&f)[N])
 {
   double p[N], a[N], dfs[N]; int n[N];
-  bool rare = false;
 #pragma unroll
   for (int i = 0; i < N; i++) {
     exp_neg_poly(x[i], p[i], n[i]);
-    rare |= alive[i] && exp_neg_is_rare(n[i]);
     if (MODEL == M_IDEAL) dfs[i] = 0.0;
     else if (MODEL == M_LIN14) dfs[i] = fma(K2 * x[i], x[i], s[i]);
     else dfs[i] = fma(s[i], rcp_fast(x[i]), K2 * x[i]);
   }
+  if (__builtin_expect(maybe_rare, 0)) {              // both sides define a[]: no register shuffling on the fast side
 #pragma unroll
-  for (int i = 0; i < N; i++) a[i] = exp_neg_fast(p[i], n[i]);
-  if (__builtin_expect(rare, 0)) {
+    for (int i = 0; i < N; i++) a[i] = exp_neg_slow(x[i], p[i], n[i]);
+  } else {
 #pragma unroll
-    for (int i = 0; i < N; i++) if (alive[i] && exp_neg_is_rare(n[i])) a[i] = exp_finite(x[i]) ? exp_neg_rare(p[i], n[i]) : 0.0;
+    for (int i = 0; i < N; i++) a[i] = exp_neg_fast(p[i], n[i]);
+  }
+  double feq[N], feqbar[N];
+  if (all_dilute) {                                    // warp-divergent only where light species meet central rapidities
+#pragma unroll
+    for (int i = 0; i < N; i++) feq[i] = occupation_bar_dilute(a[i], sign, feqbar[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i++) feq[i] = occupation_bar(a[i], sign, feqbar[i]);
   }
 #pragma unroll
   for (int i = 0; i < N; i++) {
-    double feqbar;
-    const double feq = occupation_bar(a[i], sign, feqbar);
-    if (MODEL == M_IDEAL) { f[i] = feq; continue; }
-    double df = (MODEL == M_JONAHLIN) ? fma(feqbar, dfs[i], K3) : feqbar * dfs[i];
-    df = clamp_unit(df, reg_thr);
-    f[i] = fma(feq, df, feq);
+    if (MODEL == M_IDEAL) { f[i] = feq[i]; continue; }
+    double df = (MODEL == M_JONAHLIN) ? fma(feqbar[i], dfs[i], K3) : feqbar[i] * dfs[i];
+    df = clamp_unit(df, reg_thr, one_hi);
+    f[i] = fma(feq[i], df, feq[i]);
   }
 }
 
@@ -145,6 +152,7 @@ cf_kernel(const HotParams hp)
   const double mT2 = m2 + pT2;
   const double mT = sqrt(mT2);
   const int reg_thr = hp.regulate_thr;
+  const int one_hi = hp.one_hi;                               // high word of 1.0, kept in a register (see clamp_unit)
   const long long thr = hp.outflow_thr;
   const int thr_hi = (int)(thr >> 32);                       // grouped paths test the high word of p.dsigma only
   const double *renorm = (MODEL == M_FEQMOD && hp.renorm) ? hp.renorm + (int64_t)ipart * L.n_cells_pad : nullptr;
@@ -241,20 +249,28 @@ cf_kernel(const HotParams hp)
               }
             }
           } else {
-            double xv[NPT], pv[NPT], av[NPT]; bool lv[NPT]; bool any = false;
+            double xv[NPT], pv[NPT], av[NPT]; bool any, rare, dilute;
 #pragma unroll
             for (int k = 0; k < NPT; k++) {
               const double p1 = e1 + g1[k], p2 = e2 + g2[k], p3 = e3 + g3[k];
               double E2 = fma(p1, p1, g0[k]); E2 = fma(p2, p2, E2); E2 = fma(p3, p3, E2);
               xv[k] = sqrt_fast(E2);
-              lv[k] = exp_alive_hi(xv[k]);
-              any |= lv[k];
               pv[k] = fma(w, pd[k], cpm);
             }
+            group_flags<NPT>(xv, any, rare, dilute);
+            if (DIM2) dilute = false;              // 2+1D groups are wide (light species, all eta): the extra branch costs more than it saves
             if (any) {
-              exp_neg_group<NPT>(xv, lv, av);
+              exp_neg_group<NPT>(xv, rare, av);
+              double fo[NPT], unused;
+              if (dilute) {
 #pragma unroll
-              for (int k = 0; k < NPT; k++) accumulate_alive(accj[k], pv[k], rn * occupation(av[k], sign), thr_hi, xv[k]);
+                for (int k = 0; k < NPT; k++) fo[k] = occupation_bar_dilute(av[k], sign, unused);
+              } else {
+#pragma unroll
+                for (int k = 0; k < NPT; k++) fo[k] = occupation(av[k], sign);
+              }
+#pragma unroll
+              for (int k = 0; k < NPT; k++) accumulate_pos(accj[k], pv[k], rn * fo[k], thr_hi);
             }
           }
         } else if (MODEL == M_VAH) {
@@ -275,18 +291,16 @@ cf_kernel(const HotParams hp)
                 s = fma(K2 * u, u, s);
                 const double fa = occupation(exp_neg(x), sign);
                 const double fabar = fma(-sign, fa, 1.0);
-                const double df = clamp_unit(fabar * s, reg_thr);
+                const double df = clamp_unit(fabar * s, reg_thr, one_hi);
                 accumulate_outflow(accj[k], pds, fma(fa, df, fa), thr);
               }
             }
           } else {
-            double xv[NPT], pv[NPT], sv[NPT], av[NPT]; bool lv[NPT]; bool any = false;
+            double xv[NPT], pv[NPT], sv[NPT], av[NPT]; bool any, rare, dilute;
 #pragma unroll
             for (int k = 0; k < NPT; k++) {
               const double u = a - q[k];
               xv[k] = sqrt_fast(fma(u, u, hz));
-              lv[k] = exp_alive_hi(xv[k]);
-              any |= lv[k];
               pv[k] = fma(w, pd[k], cpm);
               double s = h0 + g0[k];
               s = fma(g2[k], h2, s);
@@ -294,14 +308,23 @@ cf_kernel(const HotParams hp)
               s = fma(-g3[k], h3, s);
               sv[k] = fma(K2 * u, u, s);
             }
+            group_flags<NPT>(xv, any, rare, dilute);
+            if (DIM2) dilute = false;              // 2+1D groups are wide (light species, all eta): the extra branch costs more than it saves
             if (any) {
-              exp_neg_group<NPT>(xv, lv, av);
+              exp_neg_group<NPT>(xv, rare, av);
+              double fav[NPT], fbv[NPT];
+              if (dilute) {
+#pragma unroll
+                for (int k = 0; k < NPT; k++) fav[k] = occupation_bar_dilute(av[k], sign, fbv[k]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < NPT; k++) fav[k] = occupation_bar(av[k], sign, fbv[k]);
+              }
 #pragma unroll
               for (int k = 0; k < NPT; k++) {
-                double fabar;
-                const double fa = occupation_bar(av[k], sign, fabar);
-                const double df = clamp_unit(fabar * sv[k], reg_thr);
-                accumulate_alive(accj[k], pv[k], fma(fa, df, fa), thr_hi, xv[k]);
+                const double fa = fav[k], fabar = fbv[k];
+                const double df = clamp_unit(fabar * sv[k], reg_thr, one_hi);
+                accumulate_pos(accj[k], pv[k], fma(fa, df, fa), thr_hi);
               }
             }
           }
@@ -316,30 +339,27 @@ cf_kernel(const HotParams hp)
                 double s = h0 + g0[k];
                 s = fma(g2[k], h2, s);
                 s = fma(-g1[k], h1, s);
-                const double f = distribution<MODEL>(x, s, K2, K3, sign, reg_thr);
+                const double f = distribution<MODEL>(x, s, K2, K3, sign, reg_thr, one_hi);
                 accumulate_outflow(accj[k], pds, f, thr);
               }
             }
           } else if (SB == 3) {
             // e^{-x} = e^{-mT Ax} e^{+pT Bx}: one exponential per slot and one per phi point instead of one per evaluation
-            double xs[NPT]; bool alive[NPT]; bool any = false;
+            double xs[NPT]; bool any, rare, dilute;
 #pragma unroll
-            for (int k = 0; k < NPT; k++) { xs[k] = a - q[k]; alive[k] = exp_alive_hi(xs[k]); any |= alive[k]; }
+            for (int k = 0; k < NPT; k++) xs[k] = a - q[k];
+            group_flags<NPT>(xs, any, rare, dilute);
+            if (DIM2) dilute = false;
             if (any) {
               double pe; int ne;
               exp_neg_poly(a, pe, ne);
-              double av[NPT]; bool rare = false;
-#pragma unroll
-              for (int k = 0; k < NPT; k++) {
-                const int n = ne + fm[k];
-                const double p = pe * fq[k];
-                av[k] = exp_neg_fast(p, n);
-                rare |= alive[k] && exp_neg_is_rare(n);
-              }
+              double av[NPT];
               if (__builtin_expect(rare, 0)) {
 #pragma unroll
-                for (int k = 0; k < NPT; k++)
-                  if (alive[k] && exp_neg_is_rare(ne + fm[k])) av[k] = exp_finite(xs[k]) ? exp_neg_rare(pe * fq[k], ne + fm[k]) : 0.0;
+                for (int k = 0; k < NPT; k++) av[k] = exp_neg_slow(xs[k], pe * fq[k], ne + fm[k]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < NPT; k++) av[k] = exp_neg_fast(pe * fq[k], ne + fm[k]);
               }
 #pragma unroll
               for (int k = 0; k < NPT; k++) {
@@ -347,13 +367,15 @@ cf_kernel(const HotParams hp)
                 double s = h0 + g0[k];
                 s = fma(g2[k], h2, s);
                 s = fma(-g1[k], h1, s);
-                accumulate_alive(accj[k], pds, distribution_from_a<MODEL>(av[k], xs[k], s, K2, K3, sign, reg_thr), thr_hi, xs[k]);
+                accumulate_pos(accj[k], pds, distribution_from_a<MODEL>(av[k], xs[k], s, K2, K3, sign, reg_thr, one_hi, dilute), thr_hi);
               }
             }
           } else {
-            double xs[NPT]; bool alive[NPT]; bool any = false;
+            double xs[NPT]; bool any, rare, dilute;
 #pragma unroll
-            for (int k = 0; k < NPT; k++) { xs[k] = a - q[k]; alive[k] = exp_alive_hi(xs[k]); any |= alive[k]; }
+            for (int k = 0; k < NPT; k++) xs[k] = a - q[k];
+            group_flags<NPT>(xs, any, rare, dilute);
+            if (DIM2) dilute = false;
             if (any) {
               double sv[NPT], pv[NPT], fv[NPT];
 #pragma unroll
@@ -363,9 +385,9 @@ cf_kernel(const HotParams hp)
                 s = fma(g2[k], h2, s);
                 sv[k] = fma(-g1[k], h1, s);
               }
-              distribution_group<MODEL, NPT>(xs, alive, sv, K2, K3, sign, reg_thr, fv);
+              distribution_group<MODEL, NPT>(xs, rare, dilute, sv, K2, K3, sign, reg_thr, one_hi, fv);
 #pragma unroll
-              for (int k = 0; k < NPT; k++) accumulate_alive(accj[k], pv[k], fv[k], thr_hi, xs[k]);
+              for (int k = 0; k < NPT; k++) accumulate_pos(accj[k], pv[k], fv[k], thr_hi);
             }
           }
         }
@@ -377,36 +399,33 @@ cf_kernel(const HotParams hp)
         const double2 a0 = y0[0], a1 = y0[1], a2 = y0[2], b0 = y1[0], b1 = y1[1], b2 = y1[2];
         const double aA = mT * a0.x, cA = mT * a0.y, h0A = mT2 * a1.x, h1A = mT * a1.y, h2A = mT * a2.x, wA = a2.y;
         const double aB = mT * b0.x, cB = mT * b0.y, h0B = mT2 * b1.x, h1B = mT * b1.y, h2B = mT * b2.x, wB = b2.y;
-        double xA[NPT], xB[NPT]; bool lA[NPT], lB[NPT]; bool any = false;
+        double xv[2 * NPT]; bool any, rare, dilute;
 #pragma unroll
-        for (int k = 0; k < NPT; k++) {
-          xA[k] = aA - q[k]; xB[k] = aB - q[k];
-          lA[k] = exp_alive_hi(xA[k]); lB[k] = exp_alive_hi(xB[k]); any |= lA[k] | lB[k];
-        }
+        for (int k = 0; k < NPT; k++) { xv[k] = aA - q[k]; xv[NPT + k] = aB - q[k]; }
+        group_flags<2 * NPT>(xv, any, rare, dilute);
         if (any) {
-          double xv[2 * NPT], sv[2 * NPT], pv[2 * NPT], fv[2 * NPT]; bool lv[2 * NPT];
+          double sv[2 * NPT], pv[2 * NPT], fv[2 * NPT];
 #pragma unroll
           for (int k = 0; k < NPT; k++) {
-            xv[k] = xA[k]; xv[NPT + k] = xB[k]; lv[k] = lA[k]; lv[NPT + k] = lB[k];
             pv[k] = fma(wA, pd[k], cA); pv[NPT + k] = fma(wB, pd[k], cB);
             double s0 = h0A + g0[k], s1 = h0B + g0[k];
             s0 = fma(g2[k], h2A, s0); s1 = fma(g2[k], h2B, s1);
             sv[k] = fma(-g1[k], h1A, s0); sv[NPT + k] = fma(-g1[k], h1B, s1);
           }
-          distribution_group<MODEL, 2 * NPT>(xv, lv, sv, K2, K3, sign, reg_thr, fv);
+          distribution_group<MODEL, 2 * NPT>(xv, rare, dilute, sv, K2, K3, sign, reg_thr, one_hi, fv);
 #pragma unroll
-          for (int k = 0; k < 2 * NPT; k++) accumulate_alive(accj[k], pv[k], fv[k], thr_hi, xv[k]);
+          for (int k = 0; k < 2 * NPT; k++) accumulate_pos(accj[k], pv[k], fv[k], thr_hi);
         }
       };
       // SB == 4 (linear models, 3+1D): like SB == 1, but the aliveness test of slot j + 1 is issued before slot j is
       // evaluated, so that the skip branch of the next slot never waits for its predicate chain (DMUL, DADD, 2 ISETP)
-      auto probe = [&](int j, double (&x)[NPT], bool (&l)[NPT], bool &any) {
+      auto probe = [&](int j, double (&x)[NPT], bool &any, bool &rare, bool &dilute) {
         const double a = mT * Ys[(c * nst + j) * RY];
-        any = false;
 #pragma unroll
-        for (int k = 0; k < NPT; k++) { x[k] = a - q[k]; l[k] = exp_alive_hi(x[k]); any |= l[k]; }
+        for (int k = 0; k < NPT; k++) x[k] = a - q[k];
+        group_flags<NPT>(x, any, rare, dilute);
       };
-      auto eval_probed = [&](int j, const double (&x)[NPT], const bool (&l)[NPT], double *accj) {
+      auto eval_probed = [&](int j, const double (&x)[NPT], bool rare, bool dilute, double *accj) {
         const double2 *yr = reinterpret_cast<const double2 *>(Ys + (c * nst + j) * RY);
         const double2 v0 = yr[0], v1 = yr[1], v2 = yr[2];
         const double cpm = mT * v0.y, h0 = mT2 * v1.x, h1 = mT * v1.y, h2 = mT * v2.x, w = v2.y;
@@ -418,23 +437,23 @@ cf_kernel(const HotParams hp)
           s = fma(g2[k], h2, s);
           sv[k] = fma(-g1[k], h1, s);
         }
-        distribution_group<MODEL, NPT>(x, l, sv, K2, K3, sign, reg_thr, fv);
+        distribution_group<MODEL, NPT>(x, rare, dilute, sv, K2, K3, sign, reg_thr, one_hi, fv);
 #pragma unroll
-        for (int k = 0; k < NPT; k++) accumulate_alive(accj[k], pv[k], fv[k], thr_hi, x[k]);
+        for (int k = 0; k < NPT; k++) accumulate_pos(accj[k], pv[k], fv[k], thr_hi);
       };
       if (DIM2) {
 #pragma unroll 2
         for (int j = 0; j < nst; j++) slot(j, acc);
       } else if (SB == 4 && MODEL != M_FEQMOD && MODEL != M_VAH) {
-        double xa[NPT], xb[NPT]; bool la[NPT], lb[NPT]; bool anya, anyb = false;
-        probe(0, xa, la, anya);
+        double xa[NPT], xb[NPT]; bool anya, rarea, dila, anyb = false, rareb = false, dilb = false;
+        probe(0, xa, anya, rarea, dila);
 #pragma unroll
         for (int j = 0; j < NYT; j++) {
-          if (j + 1 < NYT) probe(j + 1, xb, lb, anyb);
-          if (anya) eval_probed(j, xa, la, acc + j * NPT);
+          if (j + 1 < NYT) probe(j + 1, xb, anyb, rareb, dilb);
+          if (anya) eval_probed(j, xa, rarea, dila, acc + j * NPT);
 #pragma unroll
-          for (int k = 0; k < NPT; k++) { xa[k] = xb[k]; la[k] = lb[k]; }
-          anya = anyb;
+          for (int k = 0; k < NPT; k++) xa[k] = xb[k];
+          anya = anyb; rarea = rareb; dila = dilb;
         }
       } else if (SB == 2 && MODEL != M_FEQMOD && MODEL != M_VAH) {
 #pragma unroll
