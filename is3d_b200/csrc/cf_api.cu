@@ -248,7 +248,7 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   int variant;
   if (opt.tile_variant >= 1 && opt.tile_variant <= 16) variant = opt.tile_variant - 1;
   else if (sum_slots) variant = (model == M_FEQMOD || model == M_VAH) ? 12 : (model == M_IDEAL ? 13 : 10);
-  else variant = (model == M_FEQMOD || model == M_VAH) ? 12 : 9;
+  else variant = (model == M_VAH) ? 12 : (model == M_FEQMOD) ? 11 : 9;
   (void)dim2_early;
   int nyt, npt, ct;
   hot_variant_shape(variant, sum_slots ? 1 : 0, &nyt, &npt, &ct);
@@ -266,6 +266,14 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
       const int32_t c = iq->category[i];
       if (c < 0 || c >= iq->n_categories) return fail(IS3D_ERR_ARGUMENT, "cell category out of range");
       count[(size_t)c]++;
+    }
+    // small categories: shorter TMA tiles keep the padding (on average (ct - 1) / 2 cells per category) below ~5 %
+    if (!sum_slots) {
+      int64_t nonempty = 0;
+      for (int64_t v : count) nonempty += (v > 0);
+      const int64_t avg = nonempty ? n_cells / nonempty : 0;
+      if (avg < 40) ct = 2; else if (avg < 80) ct = 4; else if (avg < 160) ct = 8;
+      L.ct = ct;
     }
     cat_tiles.resize(count.size());
     L.n_tiles = 0;
