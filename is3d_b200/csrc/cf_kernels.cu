@@ -132,6 +132,9 @@ cf_kernel(const HotParams hp)
   const int stage_doubles = y_doubles + p_doubles + s_doubles;
   double *stage_base = reinterpret_cast<double *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(stage_base + (size_t)kStages * stage_doubles);
+  // linear models, 3+1D: per-tile table of the lane-independent part of the shear term (see "pair table" below)
+  constexpr bool PAIR = !DIM2 && (MODEL == M_LIN14 || MODEL == M_LINCE || MODEL == M_JONAHLIN);
+  double *pair_tab = reinterpret_cast<double *>(full + kStages);
 
   // ---- task decode: blockIdx -> (group block, y tile, phi tile, cell chunk)
   const int n_bintiles = hp.n_groupblocks * L.n_ytiles * L.n_ptiles;
@@ -151,6 +154,7 @@ cf_kernel(const HotParams hp)
   const double m2 = mass * mass, pT2 = pT * pT;
   const double mT2 = m2 + pT2;
   const double mT = sqrt(mT2);
+  const double mTpT = mT * pT;
   const int reg_thr = hp.regulate_thr;
   const int one_hi = hp.one_hi;                               // high word of 1.0, kept in a register (see clamp_unit)
   const long long thr = hp.outflow_thr;
@@ -199,6 +203,18 @@ cf_kernel(const HotParams hp)
     const double *Ss = Ps + p_doubles;
     const int64_t cell_base = (t_begin + t) * CT;
 
+    // Pair table: coef pi^{mu nu} p_mu p_nu contains mT pT (R2[phi] U2[slot] - R1[phi] U1[slot]); the bracket does not depend on
+    // the lane, so the block computes it once per (cell, slot, phi) of the tile (2 FP64 ops) instead of every thread spending
+    // 2 DFMA + 2 hoisted DMUL on it per evaluation.  It also frees the registers of g1, g2, h1, h2.
+    if (PAIR) {
+      for (int w = threadIdx.x; w < CT * NYT * NPT; w += blockDim.x) {
+        const int c = w / (NYT * NPT), r = w - c * (NYT * NPT), j = r / NPT, k = r - j * NPT;
+        const double *yr = Ys + (c * nst + j) * RY, *pr = Ps + (c * NPT + k) * kRec;
+        pair_tab[w] = fma(pr[4], yr[4], -(pr[3] * yr[3]));
+      }
+      __syncthreads();
+    }
+
     for (int c = 0; c < CT; c++) {
       const double2 k01 = *reinterpret_cast<const double2 *>(Ss + c * kScal);
       const double K2 = k01.y;                                   // linear / vah: coefficient of x^2 (or x); feqmod: per-cell renorm
@@ -225,12 +241,19 @@ cf_kernel(const HotParams hp)
           q[k] = pT * v0.x;                 // pT * (cos ux + sin uy)/T
           pd[k] = pT * v0.y;                // pT * (cos dsigma_x + sin dsigma_y)
           g0[k] = fma(pT2, v1.x, K0m);      // pT^2 Qpp + (..) m^2
-          g1[k] = pT * v1.y;
-          g2[k] = pT * v2.x;
+          g1[k] = PAIR ? 0.0 : pT * v1.y;
+          g2[k] = PAIR ? 0.0 : pT * v2.x;
           g3[k] = (MODEL == M_VAH) ? pT * v2.y : 0.0;                      // pT (Wx cos + Wy sin)
           if (SB == 3) exp_neg_poly(-q[k], fq[k], fm[k]);
         }
       }
+      // delta-f polynomial without its (u.p)^2 part, linear models: mT^2 Qyy + pT^2 Qpp + (..) m^2 + mT pT (R2 U2 - R1 U1)
+      auto sterm = [&](int j, int k, double h0, double h1, double h2) -> double {
+        if (PAIR) return fma(mTpT, pair_tab[(c * NYT + j) * NPT + k], h0 + g0[k]);
+        double s = h0 + g0[k];
+        s = fma(g2[k], h2, s);
+        return fma(-g1[k], h1, s);
+      };
       auto slot = [&](int j, double *accj) {
         const double2 *yr = reinterpret_cast<const double2 *>(Ys + (c * nst + j) * RY);
         const double2 v0 = yr[0], v1 = yr[1], v2 = yr[2];
@@ -336,9 +359,7 @@ cf_kernel(const HotParams hp)
               const double x = a - q[k];
               const double pds = fma(w, pd[k], cpm);
               if (exp_finite(x)) {                           // else exp(x) overflows: f = 0 exactly
-                double s = h0 + g0[k];
-                s = fma(g2[k], h2, s);
-                s = fma(-g1[k], h1, s);
+                const double s = sterm(j, k, h0, h1, h2);
                 const double f = distribution<MODEL>(x, s, K2, K3, sign, reg_thr, one_hi);
                 accumulate_outflow(accj[k], pds, f, thr);
               }
@@ -364,9 +385,7 @@ cf_kernel(const HotParams hp)
 #pragma unroll
               for (int k = 0; k < NPT; k++) {
                 const double pds = fma(w, pd[k], cpm);
-                double s = h0 + g0[k];
-                s = fma(g2[k], h2, s);
-                s = fma(-g1[k], h1, s);
+                const double s = sterm(j, k, h0, h1, h2);
                 accumulate_pos(accj[k], pds, distribution_from_a<MODEL>(av[k], xs[k], s, K2, K3, sign, reg_thr, one_hi, dilute), thr_hi);
               }
             }
@@ -381,9 +400,7 @@ cf_kernel(const HotParams hp)
 #pragma unroll
               for (int k = 0; k < NPT; k++) {
                 pv[k] = fma(w, pd[k], cpm);
-                double s = h0 + g0[k];
-                s = fma(g2[k], h2, s);
-                sv[k] = fma(-g1[k], h1, s);
+                sv[k] = sterm(j, k, h0, h1, h2);
               }
               distribution_group<MODEL, NPT>(xs, rare, dilute, sv, K2, K3, sign, reg_thr, one_hi, fv);
 #pragma unroll
@@ -408,9 +425,7 @@ cf_kernel(const HotParams hp)
 #pragma unroll
           for (int k = 0; k < NPT; k++) {
             pv[k] = fma(wA, pd[k], cA); pv[NPT + k] = fma(wB, pd[k], cB);
-            double s0 = h0A + g0[k], s1 = h0B + g0[k];
-            s0 = fma(g2[k], h2A, s0); s1 = fma(g2[k], h2B, s1);
-            sv[k] = fma(-g1[k], h1A, s0); sv[NPT + k] = fma(-g1[k], h1B, s1);
+            sv[k] = sterm(j, k, h0A, h1A, h2A); sv[NPT + k] = sterm(j + 1, k, h0B, h1B, h2B);
           }
           distribution_group<MODEL, 2 * NPT>(xv, rare, dilute, sv, K2, K3, sign, reg_thr, one_hi, fv);
 #pragma unroll
@@ -433,9 +448,7 @@ cf_kernel(const HotParams hp)
 #pragma unroll
         for (int k = 0; k < NPT; k++) {
           pv[k] = fma(w, pd[k], cpm);
-          double s = h0 + g0[k];
-          s = fma(g2[k], h2, s);
-          sv[k] = fma(-g1[k], h1, s);
+          sv[k] = sterm(j, k, h0, h1, h2);
         }
         distribution_group<MODEL, NPT>(x, rare, dilute, sv, K2, K3, sign, reg_thr, one_hi, fv);
 #pragma unroll
@@ -606,7 +619,8 @@ static cudaError_t launch_one(const HotParams &hp, cudaStream_t st, size_t *smem
   constexpr int RY = (MODEL == M_VAH) ? kRecVah : kRec;
   const int nst = DIM2 ? L.nst : NYT;
   const size_t stage_doubles = (size_t)L.ct * nst * RY + (size_t)L.ct * NPT * kRec + (size_t)L.ct * kScal;
-  const size_t smem = kStages * stage_doubles * 8 + kStages * sizeof(uint64_t);
+  constexpr bool PAIR = !DIM2 && (MODEL == M_LIN14 || MODEL == M_LINCE || MODEL == M_JONAHLIN);
+  const size_t smem = kStages * stage_doubles * 8 + kStages * sizeof(uint64_t) + (PAIR ? (size_t)L.ct * NYT * NPT * 8 : 0);
   if (smem_out) *smem_out = smem;
   auto kern = cf_kernel<MODEL, NYT, NPT, DIM2, MINB, SB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

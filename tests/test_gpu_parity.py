@@ -279,3 +279,32 @@ def test_in_memory_surface_entry(fx):
         assert rc == 0
         assert compare(dN, gold["dN"])["ok"]
         assert os.path.getsize(os.path.join(wd, "results", "dN_pTdpTdphidy.dat")) > 0
+
+
+# ---------------------------------------------------------------------------------------- BASELINE size, size-independent properties
+def test_full_size_cfg3_properties(fx):
+    """BASELINE configs[2] at full size (1 M cells x 305 species x 16128 bins = 4.9e12 evaluations per run): the oracle cannot
+    run this, so check what must hold at any size -- additivity over a split of the surface and invariance under a
+    permutation of the cells (different chunk boundaries and summation order), both to 1e-12."""
+    import torch
+    n = 1_000_000
+    cells = synthetic.columns_to_cells(synthetic.surface_vh(n, synthetic.SEEDS["cfg3"]), 1)
+    sp = tables.species(fx, 1, "chosen_urqmd"); g = tables.grid(fx); tab = tables.df_tables(fx, 1)
+    fl = tables.flags(df_mode=1, dimension=3)
+    keys = ("tau", "eta", "dat", "dax", "day", "dan", "ux", "uy", "un", "T", "P", "E", "pixx", "pixy", "pixn", "piyy", "piyn", "bulkPi")
+    dev = {k: torch.from_numpy(np.ascontiguousarray(cells[k])).cuda() for k in keys}
+    whole, st = api.smooth_spectra(fl, dev, sp, g, tab, None, memory="device")
+    assert st["evaluations"] == n * 305 * 16128 and st["cells_skipped_udsigma"] == 0
+    cut = 371_293
+    parts = torch.zeros_like(whole)
+    api.smooth_spectra(fl, {k: v[:cut] for k, v in dev.items()}, sp, g, tab, None, memory="device", out=parts)
+    api.smooth_spectra(fl, {k: v[cut:].contiguous() for k, v in dev.items()}, sp, g, tab, None, memory="device", out=parts)   # ADDS into out
+    perm = torch.from_numpy(np.random.default_rng(5).permutation(n)).cuda()
+    shuffled, _ = api.smooth_spectra(fl, {k: v[perm].contiguous() for k, v in dev.items()}, sp, g, tab, None, memory="device")
+    w = whole.cpu().numpy()
+    assert np.all(w >= 0.0) and np.isfinite(w).all() and (w > 0).mean() > 0.99
+    for other in (parts, shuffled):
+        o = other.cpu().numpy()
+        assert np.array_equal(o == 0.0, w == 0.0)
+        nz = w != 0.0
+        assert np.max(np.abs(o[nz] - w[nz]) / w[nz]) < 1e-12
