@@ -248,7 +248,7 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   int variant;
   if (opt.tile_variant >= 1 && opt.tile_variant <= 16) variant = opt.tile_variant - 1;
   else if (sum_slots) variant = (model == M_FEQMOD || model == M_VAH) ? 12 : (model == M_IDEAL ? 13 : 10);
-  else variant = (model == M_VAH) ? 12 : (model == M_FEQMOD) ? 11 : 9;
+  else variant = (model == M_VAH || model == M_FEQMOD) ? 11 : 9;
   (void)dim2_early;
   int nyt, npt, ct;
   hot_variant_shape(variant, sum_slots ? 1 : 0, &nyt, &npt, &ct);

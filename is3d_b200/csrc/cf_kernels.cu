@@ -11,10 +11,10 @@
 //   grid      bin tiles x cell chunks; every block writes its partial spectra to partial[chunk][bin] (no atomics),
 //             reduce_kernel sums the chunks in a fixed order and adds the result into the caller's array.
 //
-// Per evaluation (df_mode 1): 34 FP64-pipe instructions (u.p, p.dsigma, 5 for the delta-f polynomial, 15 for
-// exp(-x), 5 for the Bose/Fermi factor, 7 for regulation, f and the outflow-guarded accumulate) against the 85
-// flops of the reference's inner loop -- cosh/sinh, the divisions and the tensor contraction
-// are hoisted into the per-cell records by cf_prepare.cu.
+// Per evaluation (df_mode 1): ~22 FP64-pipe instructions in a fully alive group (u.p 1, p.dsigma 1, delta-f polynomial 4,
+// exp(-x) 9 with the shared-memory table, Bose/Fermi factor 3 (dilute) or 5, df, f, accumulate 3, + ~1 of amortised hoists)
+// against the 85 flops of the reference's inner loop -- cosh/sinh, the divisions and the tensor contraction
+// are hoisted into the per-cell records by cf_prepare.cu, the lane-independent shear cross term into a per-tile pair table.
 #include "cf_internal.h"
 #include "cf_device.cuh"
 
@@ -133,7 +133,7 @@ cf_kernel(const HotParams hp)
   double *stage_base = reinterpret_cast<double *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(stage_base + (size_t)kStages * stage_doubles);
   // linear models, 3+1D: per-tile table of the lane-independent part of the shear term (see "pair table" below)
-  constexpr bool PAIR = !DIM2 && (MODEL == M_LIN14 || MODEL == M_LINCE || MODEL == M_JONAHLIN);
+  constexpr bool PAIR = !DIM2 && (MODEL == M_LIN14 || MODEL == M_LINCE || MODEL == M_JONAHLIN || MODEL == M_VAH);
   double *pair_tab = reinterpret_cast<double *>(full + kStages);
 
   // ---- task decode: blockIdx -> (group block, y tile, phi tile, cell chunk)
@@ -210,7 +210,9 @@ cf_kernel(const HotParams hp)
       for (int w = threadIdx.x; w < CT * NYT * NPT; w += blockDim.x) {
         const int c = w / (NYT * NPT), r = w - c * (NYT * NPT), j = r / NPT, k = r - j * NPT;
         const double *yr = Ys + (c * nst + j) * RY, *pr = Ps + (c * NPT + k) * kRec;
-        pair_tab[w] = fma(pr[4], yr[4], -(pr[3] * yr[3]));
+        double t = fma(pr[4], yr[4], -(pr[3] * yr[3]));
+        if (MODEL == M_VAH) t = fma(-pr[5], yr[5], t);              // - c3 (z.p) W_perp.p, the third mixed term of the anisotropic df
+        pair_tab[w] = t;
       }
       __syncthreads();
     }
@@ -243,7 +245,7 @@ cf_kernel(const HotParams hp)
           g0[k] = fma(pT2, v1.x, K0m);      // pT^2 Qpp + (..) m^2
           g1[k] = PAIR ? 0.0 : pT * v1.y;
           g2[k] = PAIR ? 0.0 : pT * v2.x;
-          g3[k] = (MODEL == M_VAH) ? pT * v2.y : 0.0;                      // pT (Wx cos + Wy sin)
+          g3[k] = (MODEL == M_VAH && !PAIR) ? pT * v2.y : 0.0;             // pT (Wx cos + Wy sin)
           if (SB == 3) exp_neg_poly(-q[k], fq[k], fm[k]);
         }
       }
@@ -307,10 +309,9 @@ cf_kernel(const HotParams hp)
               const double x = sqrt_fast(fma(u, u, hz));                   // E_a / Lambda
               const double pds = fma(w, pd[k], cpm);
               if (exp_finite(x)) {
-                double s = h0 + g0[k];
-                s = fma(g2[k], h2, s);
-                s = fma(-g1[k], h1, s);
-                s = fma(-g3[k], h3, s);
+                double s;
+                if (PAIR) s = fma(mTpT, pair_tab[(c * NYT + j) * NPT + k], h0 + g0[k]);
+                else { s = h0 + g0[k]; s = fma(g2[k], h2, s); s = fma(-g1[k], h1, s); s = fma(-g3[k], h3, s); }
                 s = fma(K2 * u, u, s);
                 const double fa = occupation(exp_neg(x), sign);
                 const double fabar = fma(-sign, fa, 1.0);
@@ -325,10 +326,9 @@ cf_kernel(const HotParams hp)
               const double u = a - q[k];
               xv[k] = sqrt_fast(fma(u, u, hz));
               pv[k] = fma(w, pd[k], cpm);
-              double s = h0 + g0[k];
-              s = fma(g2[k], h2, s);
-              s = fma(-g1[k], h1, s);
-              s = fma(-g3[k], h3, s);
+              double s;
+              if (PAIR) s = fma(mTpT, pair_tab[(c * NYT + j) * NPT + k], h0 + g0[k]);
+              else { s = h0 + g0[k]; s = fma(g2[k], h2, s); s = fma(-g1[k], h1, s); s = fma(-g3[k], h3, s); }
               sv[k] = fma(K2 * u, u, s);
             }
             group_flags<NPT>(xv, any, rare, dilute);
@@ -619,7 +619,7 @@ static cudaError_t launch_one(const HotParams &hp, cudaStream_t st, size_t *smem
   constexpr int RY = (MODEL == M_VAH) ? kRecVah : kRec;
   const int nst = DIM2 ? L.nst : NYT;
   const size_t stage_doubles = (size_t)L.ct * nst * RY + (size_t)L.ct * NPT * kRec + (size_t)L.ct * kScal;
-  constexpr bool PAIR = !DIM2 && (MODEL == M_LIN14 || MODEL == M_LINCE || MODEL == M_JONAHLIN);
+  constexpr bool PAIR = !DIM2 && (MODEL == M_LIN14 || MODEL == M_LINCE || MODEL == M_JONAHLIN || MODEL == M_VAH);
   const size_t smem = kStages * stage_doubles * 8 + kStages * sizeof(uint64_t) + (PAIR ? (size_t)L.ct * NYT * NPT * 8 : 0);
   if (smem_out) *smem_out = smem;
   auto kern = cf_kernel<MODEL, NYT, NPT, DIM2, MINB, SB>;
