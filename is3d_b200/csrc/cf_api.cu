@@ -250,8 +250,8 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   else if (sum_slots) variant = (model == M_FEQMOD || model == M_VAH) ? 12 : (model == M_IDEAL ? 13 : 10);
   else variant = (model == M_VAH || model == M_FEQMOD) ? 11 : 9;
   (void)dim2_early;
-  int nyt, npt, ct;
-  hot_variant_shape(variant, sum_slots ? 1 : 0, &nyt, &npt, &ct);
+  int nyt, npt, ct, max_warps;
+  hot_variant_shape(variant, sum_slots ? 1 : 0, &nyt, &npt, &ct, &max_warps);
   L.nst = sum_slots ? L.n_slots : nyt;
   L.n_ytiles = sum_slots ? 1 : (L.n_slots + nyt - 1) / nyt;
   L.npt = npt; L.n_ptiles = (L.n_phi + npt - 1) / npt;
@@ -285,10 +285,10 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
 
   const int n_pairs = sp->n * gr->n_pT;
   const int n_groups = (n_pairs + 31) / 32;
-  int n_warps = kMaxWarps;                                  // widest block whose padding wastes <= 4 % of the warps
+  int n_warps = max_warps;                                  // widest block whose padding wastes <= 4 % of the warps
   {
     int best = 1 << 30;
-    for (int w = kMaxWarps; w >= 1; w--) {
+    for (int w = max_warps; w >= 1; w--) {
       const int launched = ((n_groups + w - 1) / w) * w;
       if ((launched - n_groups) * 25 <= launched) { n_warps = w; break; }
       if (launched < best) { best = launched; n_warps = w; }
@@ -591,9 +591,11 @@ extern "C" int is3d_b200_spacetime_distributions(const is3d_flags *fl, const is3
   const double *tau = sf->tau, *x = sf->x, *y = sf->y;
   if (device_mem && n > 0) {
     hbuf.resize((size_t)n * 3);
-    if (cudaMemcpy(hbuf.data(), sf->tau, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
-        cudaMemcpy(hbuf.data() + n, sf->x, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
-        cudaMemcpy(hbuf.data() + 2 * n, sf->y, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+    cudaStream_t cs = (cudaStream_t)opt_in->stream;          // ordered after whatever produced the arrays on the caller's stream
+    if (cudaMemcpyAsync(hbuf.data(), sf->tau, (size_t)n * 8, cudaMemcpyDeviceToHost, cs) != cudaSuccess ||
+        cudaMemcpyAsync(hbuf.data() + n, sf->x, (size_t)n * 8, cudaMemcpyDeviceToHost, cs) != cudaSuccess ||
+        cudaMemcpyAsync(hbuf.data() + 2 * n, sf->y, (size_t)n * 8, cudaMemcpyDeviceToHost, cs) != cudaSuccess ||
+        cudaStreamSynchronize(cs) != cudaSuccess)
       return fail(IS3D_ERR_CUDA, "device -> host copy of tau, x, y failed");
     tau = hbuf.data(); x = tau + n; y = x + n;
   }

@@ -10,6 +10,8 @@ constexpr int kRec = 6;          // doubles per phi record (and per slot record,
 constexpr int kRecVah = 8;       // doubles per slot record of the anisotropic model
 constexpr int kScal = 4;         // doubles per per-cell scalar record
 constexpr int kMaxWarps = 4;     // warps per hot-kernel block (each warp = 32 consecutive (species, pT) pairs)
+// variants with MINB >= 7 run 2-warp blocks (register cap 144 at 7 blocks/SM = 14 warps/SM instead of 12)
+constexpr int block_warps(int minb) { return minb >= 7 ? 2 : kMaxWarps; }
 constexpr int kStages = 4;       // TMA pipeline depth
 
 // Device-side view of the raw surface (GeV/fm units), NULL where switched off
@@ -95,6 +97,6 @@ cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, i
 // integ -> out[unit][species], unit = chunk (mode 1) or slot (mode 2, summed over chunks)
 cudaError_t launch_integ_reduce(const HotParams &hp, int n_units, double *out, cudaStream_t st);
 cudaError_t launch_fp64_peak(double *sink, int iters, cudaStream_t st, int *blocks, int *threads, long long *dfma_per_thread);
-void hot_variant_shape(int variant, int dim2, int *nyt, int *npt, int *ct);
+void hot_variant_shape(int variant, int dim2, int *nyt, int *npt, int *ct, int *max_warps);
 
 }  // namespace is3d

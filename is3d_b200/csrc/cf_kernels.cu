@@ -120,7 +120,7 @@ __device__ __forceinline__ void distribution_group(const double (&x)[N], bool ma
 }
 
 template <int MODEL, int NYT, int NPT, bool DIM2, int MINB, int SB>
-__global__ void __launch_bounds__(kMaxWarps * 32, MINB)
+__global__ void __launch_bounds__(block_warps(MINB) * 32, MINB)
 cf_kernel(const HotParams hp)
 {
   constexpr int RY = (MODEL == M_VAH) ? kRecVah : kRec;       // doubles per slot record
@@ -598,18 +598,18 @@ cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, i
 // Variants >= 8 are compiled for the 14-moment model only (tuning sweep) and fall back to variant 0 elsewhere.
 struct Shape { int nyt, npt, ct, minb, sb; };
 static const Shape kShapes3D[] = {
-  {7, 1, 16, 6, 0}, {7, 3, 16, 3, 0}, {7, 3, 16, 5, 4}, {7, 4, 16, 3, 4}, {7, 2, 16, 6, 4}, {3, 6, 16, 3, 0}, {7, 6, 16, 2, 4}, {7, 3, 16, 4, 0},
+  {7, 3, 8, 7, 4}, {7, 3, 8, 7, 1}, {7, 3, 16, 5, 4}, {7, 4, 16, 3, 4}, {7, 2, 16, 6, 4}, {3, 6, 16, 3, 0}, {7, 6, 16, 2, 4}, {7, 3, 16, 4, 0},
   {7, 3, 16, 4, 3}, {7, 3, 16, 3, 4}, {7, 3, 16, 3, 3}, {7, 3, 16, 4, 1}, {7, 3, 16, 3, 1}, {7, 4, 16, 4, 1}, {7, 2, 16, 6, 1}, {7, 3, 16, 4, 4}};
 static const Shape kShapes2D[] = {
   {1, 3, 1, 4, 0}, {1, 4, 1, 4, 0}, {1, 6, 1, 3, 0}, {1, 8, 1, 3, 0}, {1, 2, 1, 5, 0}, {1, 12, 1, 2, 0}, {1, 4, 1, 3, 0}, {1, 1, 1, 6, 0},
   {1, 6, 1, 3, 3}, {1, 3, 1, 4, 1}, {1, 4, 1, 4, 3}, {1, 4, 1, 3, 1}, {1, 6, 1, 3, 1}, {1, 8, 1, 3, 3}, {1, 3, 1, 5, 1}, {1, 12, 1, 2, 3}};
 constexpr int kNumVariants = 16;
 
-void hot_variant_shape(int variant, int dim2, int *nyt, int *npt, int *ct)
+void hot_variant_shape(int variant, int dim2, int *nyt, int *npt, int *ct, int *max_warps)
 {
   if (variant < 0 || variant >= kNumVariants) variant = 0;
   const Shape &s = dim2 ? kShapes2D[variant] : kShapes3D[variant];
-  *nyt = s.nyt; *npt = s.npt; *ct = s.ct;
+  *nyt = s.nyt; *npt = s.npt; *ct = s.ct; *max_warps = block_warps(s.minb);
 }
 
 template <int MODEL, int NYT, int NPT, bool DIM2, int MINB, int SB>
@@ -662,7 +662,7 @@ static cudaError_t launch_model(const HotParams &hp, int variant, cudaStream_t s
     return launch_one<MODEL, 1, 3, true, 4, 0>(hp, st, smem_out);
   }
   switch (variant) {
-    case 1: return launch_one<MODEL, 7, 3, false, 3, 0>(hp, st, smem_out);
+    case 1: return launch_one<MODEL, 7, 3, false, 7, 1>(hp, st, smem_out);
     case 2: return launch_one<MODEL, 7, 3, false, 5, 4>(hp, st, smem_out);
     case 3: return launch_one<MODEL, 7, 4, false, 3, 4>(hp, st, smem_out);
     case 4: return launch_one<MODEL, 7, 2, false, 6, 4>(hp, st, smem_out);
@@ -684,7 +684,7 @@ static cudaError_t launch_model(const HotParams &hp, int variant, cudaStream_t s
       default: break;
     }
   }
-  return launch_one<MODEL, 7, 1, false, 6, 0>(hp, st, smem_out);
+  return launch_one<MODEL, 7, 3, false, 7, 4>(hp, st, smem_out);
 }
 
 cudaError_t launch_hot(int model, const HotParams &hp, int variant, cudaStream_t st, size_t *smem_out)
