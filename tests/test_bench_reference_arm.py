@@ -22,7 +22,7 @@ def test_reference_sample_small():
 
 def test_reference_arm_prints_one_json_line(monkeypatch):
     env = dict(os.environ, RANK="0", WORLD_SIZE="1", OMP_NUM_THREADS="2")
-    code = ("import bench, sys; bench.reference_sample.__defaults__ = (40, 1, 2, 1); "
+    code = ("import bench, sys; bench.reference_sample.__defaults__ = (40, 1, 2, 1, 1); "
             "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '1']; bench.main()")
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
@@ -33,6 +33,14 @@ def test_reference_arm_prints_one_json_line(monkeypatch):
     env["RANK"] = "1"
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_sample_operation_0():
+    import bench
+    r = bench.reference_sample("cfg3", cells=160, n_species=2, threads=2, operation=0)      # 40 cells after the operation-0 cut
+    assert r["evaluations"] == 40 * 2 * 32 * 24 * 21 and r["value"] > 1e5
+    if r["kind"] == "reference":
+        assert r["cores"] == 1 and "no OpenMP pragma" in r["sample"]
 
 
 def test_bench_refuses_without_gpu():
