@@ -134,6 +134,8 @@ cf_kernel(const HotParams hp)
   uint64_t *full = reinterpret_cast<uint64_t *>(stage_base + (size_t)kStages * stage_doubles);
   // linear models, 3+1D: per-tile table of the lane-independent part of the shear term (see "pair table" below)
   constexpr bool PAIR = !DIM2 && (MODEL == M_LIN14 || MODEL == M_LINCE || MODEL == M_JONAHLIN || MODEL == M_VAH);
+  // modified equilibrium, 3+1D: the same table holds 2 v[slot].w[phi] for the expanded form of |p'|^2 (well-conditioned cells)
+  constexpr bool PAIRF = !DIM2 && MODEL == M_FEQMOD;
   double *pair_tab = reinterpret_cast<double *>(full + kStages);
 
   // ---- task decode: blockIdx -> (group block, y tile, phi tile, cell chunk)
@@ -206,12 +208,17 @@ cf_kernel(const HotParams hp)
     // Pair table: coef pi^{mu nu} p_mu p_nu contains mT pT (R2[phi] U2[slot] - R1[phi] U1[slot]); the bracket does not depend on
     // the lane, so the block computes it once per (cell, slot, phi) of the tile (2 FP64 ops) instead of every thread spending
     // 2 DFMA + 2 hoisted DMUL on it per evaluation.  It also frees the registers of g1, g2, h1, h2.
-    if (PAIR) {
+    if (PAIR || PAIRF) {
       for (int w = threadIdx.x; w < CT * NYT * NPT; w += blockDim.x) {
         const int c = w / (NYT * NPT), r = w - c * (NYT * NPT), j = r / NPT, k = r - j * NPT;
         const double *yr = Ys + (c * nst + j) * RY, *pr = Ps + (c * NPT + k) * kRec;
-        double t = fma(pr[4], yr[4], -(pr[3] * yr[3]));
-        if (MODEL == M_VAH) t = fma(-pr[5], yr[5], t);              // - c3 (z.p) W_perp.p, the third mixed term of the anisotropic df
+        double t;
+        if (PAIRF) {
+          t = 2.0 * fma(pr[2], yr[2], fma(pr[1], yr[1], pr[0] * yr[0]));      // 2 v.w
+        } else {
+          t = fma(pr[4], yr[4], -(pr[3] * yr[3]));
+          if (MODEL == M_VAH) t = fma(-pr[5], yr[5], t);            // - c3 (z.p) W_perp.p, the third mixed term of the anisotropic df
+        }
         pair_tab[w] = t;
       }
       __syncthreads();
@@ -225,6 +232,9 @@ cf_kernel(const HotParams hp)
       const double K0m = k01.x * m2;
       double rn = 0.0;
       if (MODEL == M_FEQMOD) rn = renorm ? __ldg(renorm + cell_base + c) : K2;
+      // feqmod: |p'|^2 = mT^2 |v|^2 + pT^2 |w|^2 + 2 mT pT v.w may be used where A^-1 does not amplify (flag set by the prepare
+      // kernel, warp-uniform); elsewhere p' is formed component-wise, which keeps the rounding of ill-conditioned cells in parity
+      const bool expanded = PAIRF && Ss[c * kScal + 2] != 0.0;
 
       // phi hoists: a few multiplies per (cell, phi), reused by every slot
       double q[NPT], pd[NPT], g0[NPT], g1[NPT], g2[NPT], g3[NPT];
@@ -238,6 +248,7 @@ cf_kernel(const HotParams hp)
           // amplify rounding by the square of A^-1's largest eigenvalue (cells with detA << 1)
           g1[k] = pT * v0.x; g2[k] = pT * v0.y; g3[k] = pT * v1.x;         // pT w
           g0[k] = K0m;                                                     // (m/T_mod)^2
+          if (PAIRF) fq[k] = fma(pT2, v1.y, K0m);                          // pT^2 |w|^2 + (m/T_mod)^2 (expanded form; fq is free here)
           pd[k] = pT * v2.x; q[k] = 0.0;
         } else {
           q[k] = pT * v0.x;                 // pT * (cos ux + sin uy)/T
@@ -275,13 +286,20 @@ cf_kernel(const HotParams hp)
             }
           } else {
             double xv[NPT], pv[NPT], av[NPT]; bool any, rare, dilute;
+            if (expanded) {
+              const double Aj = mT2 * v1.y;                                // mT^2 |v|^2
 #pragma unroll
-            for (int k = 0; k < NPT; k++) {
-              const double p1 = e1 + g1[k], p2 = e2 + g2[k], p3 = e3 + g3[k];
-              double E2 = fma(p1, p1, g0[k]); E2 = fma(p2, p2, E2); E2 = fma(p3, p3, E2);
-              xv[k] = sqrt_fast(E2);
-              pv[k] = fma(w, pd[k], cpm);
+              for (int k = 0; k < NPT; k++) xv[k] = sqrt_fast(fma(mTpT, pair_tab[(c * NYT + j) * NPT + k], Aj + fq[k]));
+            } else {
+#pragma unroll
+              for (int k = 0; k < NPT; k++) {
+                const double p1 = e1 + g1[k], p2 = e2 + g2[k], p3 = e3 + g3[k];
+                double E2 = fma(p1, p1, g0[k]); E2 = fma(p2, p2, E2); E2 = fma(p3, p3, E2);
+                xv[k] = sqrt_fast(E2);
+              }
             }
+#pragma unroll
+            for (int k = 0; k < NPT; k++) pv[k] = fma(w, pd[k], cpm);
             group_flags<NPT>(xv, any, rare, dilute);
             if (DIM2) dilute = false;              // 2+1D groups are wide (light species, all eta): the extra branch costs more than it saves
             if (any) {
@@ -619,7 +637,7 @@ static cudaError_t launch_one(const HotParams &hp, cudaStream_t st, size_t *smem
   constexpr int RY = (MODEL == M_VAH) ? kRecVah : kRec;
   const int nst = DIM2 ? L.nst : NYT;
   const size_t stage_doubles = (size_t)L.ct * nst * RY + (size_t)L.ct * NPT * kRec + (size_t)L.ct * kScal;
-  constexpr bool PAIR = !DIM2 && (MODEL == M_LIN14 || MODEL == M_LINCE || MODEL == M_JONAHLIN || MODEL == M_VAH);
+  constexpr bool PAIR = !DIM2 && (MODEL == M_LIN14 || MODEL == M_LINCE || MODEL == M_JONAHLIN || MODEL == M_VAH || MODEL == M_FEQMOD);
   const size_t smem = kStages * stage_doubles * 8 + kStages * sizeof(uint64_t) + (PAIR ? (size_t)L.ct * NYT * NPT * 8 : 0);
   if (smem_out) *smem_out = smem;
   auto kern = cf_kernel<MODEL, NYT, NPT, DIM2, MINB, SB>;

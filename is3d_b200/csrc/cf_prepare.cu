@@ -376,6 +376,12 @@ prepare_feqmod_kernel(RawCells cells, PrepTables tab, Layout L, int include_shea
             sL[0] = -dlam / (T * T); sL[1] = dlam; sL[2] = dz - 3.0 * dlam;
           }
           sF[0] = c.invTmod * c.invTmod;
+          // well-conditioned momentum rescaling (Frobenius norm of A^-1 <= 3, identity: 1.73): the hot kernel may expand |p'|^2
+          {
+            double fro = 0.0;
+            for (int q9 = 0; q9 < 9; q9++) fro += c.Ainv[q9] * c.Ainv[q9];
+            sF[2] = (!breaks && fro <= 9.0) ? 1.0 : 0.0;
+          }
           // renormalisation: Jonah z / detA per cell; Mike per (cell, species) in renorm_kernel
           double rn = 1.0;
           if (include_bulk && DFM == 4) rn = z;
