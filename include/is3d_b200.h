@@ -170,6 +170,21 @@ int is3d_b200_vah_anisotropy(int64_t n, const double *T_fm, const double *P_fm, 
 int is3d_b200_vah_coefficients(int32_t nL, int32_t naL, const double *L_fm, const double *aL_grid, const double *c0, const double *c1,
                                const double *c2, const double *c3, const double *c4, int64_t n, const double *Lambda_GeV,
                                const double *aL, double *o0, double *o1, double *o2, double *o3, double *o4);
+/* ---- sampler mean yield -----------------------------------------------------------------------
+ * is3d_b200_particle_densities: n_eq, dn_bulk, dn_diff per species at the surface averages avg5 = (T, E, P, muB, nB) -- what
+ * Deltaf_Data::compute_particle_densities (deltafReader.cpp:536-650) stores in particle_info.  Host computation; rootK/weightK are
+ * the alpha = K rows of tables/gla_roots_weights_32_points.txt (alpha = 3 only for df_mode 1).
+ * is3d_b200_mean_yield: EmissionFunctionArray::calculate_total_yield (emissionfunction_sampling_kernels.cpp:653-831) for the
+ * chosen species' densities: sum over cells with u.dsigma > 0 of u.dsigma (n_eq + Pi dn_bulk) (df_mode 1-3) or
+ * u.dsigma z(Pi/P) n_eq (df_mode 4), times 2 y_cut in 2+1D.  include_baryon = 0 only.  The surface reduction runs on the GPU. */
+int is3d_b200_particle_densities(int32_t n, const double *mass, const double *degeneracy, const double *baryon, const double *sign,
+                                 const double *avg5, int32_t df_mode, const is3d_df_tables *df, int32_t n_points,
+                                 const double *root1, const double *weight1, const double *root2, const double *weight2,
+                                 const double *root3, const double *weight3, double *neq, double *dn_bulk, double *dn_diff);
+int is3d_b200_mean_yield(const is3d_flags *flags, const is3d_surface *surface, int32_t n_species, const double *neq,
+                         const double *dn_bulk, const is3d_df_tables *df, double y_cut, const is3d_options *options,
+                         double *Ntot, is3d_stats *stats);
+
 /* Writers only: produce the results/ files of `workdir` from a spectra array in the reference layout. */
 int is3d_b200_write_results(const char *workdir, const double *dN, int64_t n);
 /* Host-layer inspection without GPU work: dumps what the readers derived (named double records) to out_path. */

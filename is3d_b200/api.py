@@ -321,3 +321,55 @@ def spacetime_distributions(flags, cells, species, grid, df_tables, laguerre, bi
     _check(f(C.byref(fl), C.byref(sf), C.byref(sp), C.byref(g), C.byref(dft), C.byref(la), C.byref(b), C.byref(opt),
              C.byref(res), C.byref(st)))
     return out, st.as_dict()
+
+
+def particle_densities(species, avg5, df_mode, df_tables, laguerre3):
+    """(n_eq, dn_bulk, dn_diff) per species at the surface averages avg5 = (T, E, P, muB, nB) (host computation in the C++ layer).
+
+    laguerre3: dict root1, weight1, root2, weight2, root3, weight3 (alpha = 1, 2, 3 rows of the Gauss-Laguerre table)."""
+    m = _Marshal(False)
+    n = len(species["mass"])
+    dft = DfTables(); dft.n_T = len(df_tables["T"])
+    for k in DF_FIELDS:
+        if df_tables.get(k) is not None:
+            setattr(dft, k, m.host(df_tables[k]))
+    neq = np.zeros(n); bulk = np.zeros(n); diff = np.zeros(n)
+    f = lib().is3d_b200_particle_densities
+    f.restype = C.c_int
+    f.argtypes = [C.c_int32, _D, _D, _D, _D, _D, C.c_int32, C.POINTER(DfTables), C.c_int32, _D, _D, _D, _D, _D, _D, _D, _D, _D]
+    rc = f(n, m.host(species["mass"]), m.host(species["degeneracy"]), m.host(species["baryon"]), m.host(species["sign"]), m.host(avg5),
+           int(df_mode), C.byref(dft), len(laguerre3["root1"]), m.host(laguerre3["root1"]), m.host(laguerre3["weight1"]),
+           m.host(laguerre3["root2"]), m.host(laguerre3["weight2"]), m.host(laguerre3["root3"]), m.host(laguerre3["weight3"]),
+           neq.ctypes.data_as(_D), bulk.ctypes.data_as(_D), diff.ctypes.data_as(_D))
+    if rc:
+        raise Is3dError(rc, lib().is3d_b200_host_error().decode() or lib().is3d_b200_strerror(rc).decode())
+    return neq, bulk, diff
+
+
+def mean_yield(flags, cells, neq, dn_bulk, df_tables=None, y_cut=5.0, memory="host", stream=None):
+    """Call is3d_b200_mean_yield (the sampler's total-yield estimate); returns (Ntot, stats dict)."""
+    device = (memory == "device")
+    m = _Marshal(device)
+    sf = Surface()
+    sf.n_cells = len(cells["tau"]) if not _is_torch(cells["tau"]) else int(cells["tau"].numel())
+    for k in ("tau", "ux", "uy", "un", "dat", "dax", "day", "dan", "bulkPi", "P"):
+        if k in cells and cells[k] is not None:
+            setattr(sf, k, m.cells(cells[k]))
+    dft = DfTables()
+    if df_tables is not None and df_tables.get("jonah_x") is not None:
+        dft.n_jonah = len(df_tables["jonah_x"])
+        dft.jonah_x = m.host(df_tables["jonah_x"]); dft.jonah_lambda2 = m.host(df_tables["jonah_lambda2"])
+        dft.jonah_z = m.host(df_tables["jonah_z"]); dft.bulkPi_over_Peq_max = float(df_tables["bulkPi_over_Peq_max"])
+    if device and stream is None:
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+    opt = Options(); opt.memory = 1 if device else 0; opt.stream = C.c_void_p(stream or 0)
+    st = Stats(); out = C.c_double(0.0)
+    f = lib().is3d_b200_mean_yield
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(Flags), C.POINTER(Surface), C.c_int32, _D, _D, C.POINTER(DfTables), C.c_double, C.POINTER(Options),
+                  C.POINTER(C.c_double), C.POINTER(Stats)]
+    fl = make_flags(flags)
+    _check(f(C.byref(fl), C.byref(sf), len(neq), m.host(neq), m.host(dn_bulk) if dn_bulk is not None else None, C.byref(dft),
+             float(y_cut), C.byref(opt), C.byref(out), C.byref(st)))
+    return out.value, st.as_dict()

@@ -658,3 +658,96 @@ extern "C" int is3d_b200_spacetime_distributions(const is3d_flags *fl, const is3
   return IS3D_OK;
 }
 
+// Sampler mean yield (calculate_total_yield, emissionfunction_sampling_kernels.cpp:653-831) from per-species densities
+extern "C" int is3d_b200_mean_yield(const is3d_flags *fl, const is3d_surface *sf, int32_t n_species, const double *neq,
+                                    const double *dn_bulk, const is3d_df_tables *df, double y_cut, const is3d_options *opt_in,
+                                    double *Ntot_out, is3d_stats *stats)
+{
+  if (!fl || !sf || !neq || !Ntot_out || n_species <= 0) return fail(IS3D_ERR_ARGUMENT, "NULL argument");
+  if (fl->df_mode < 1 || fl->df_mode > 4) return fail(IS3D_ERR_ARGUMENT, "df_mode must be 1..4");
+  if (fl->mode == 2) return fail(IS3D_ERR_UNSUPPORTED, "the sampler has no anisotropic-hydro yield estimate");
+  if (fl->include_baryon) return fail(IS3D_ERR_UNSUPPORTED, "include_baryon = 1 (SURVEY R8)");
+  if (fl->df_mode != 4 && !dn_bulk) return fail(IS3D_ERR_ARGUMENT, "df_mode 1-3 need the bulk density corrections");
+  if (fl->df_mode == 4 && (!df || df->n_jonah < 3 || !df->jonah_x || !df->jonah_z)) return fail(IS3D_ERR_ARGUMENT, "df_mode 4 needs the Jonah z table");
+  if (!g_init) { int rc = is3d_b200_init(); if (rc) return rc; }
+  std::lock_guard<std::mutex> lk(g_mutex);
+  is3d_options opt; memset(&opt, 0, sizeof(opt));
+  if (opt_in) opt = *opt_in;
+  cudaStream_t st = (cudaStream_t)opt.stream;
+  const int64_t n = sf->n_cells;
+  if (n < 0) return fail(IS3D_ERR_ARGUMENT, "negative cell count");
+  const bool bk = fl->include_bulk_deltaf != 0;
+  const double *src[10] = {sf->tau, sf->ux, sf->uy, sf->un, sf->dat, sf->dax, sf->day, sf->dan, sf->bulkPi, sf->P};
+  const bool need[10] = {true, true, true, true, true, true, true, true, bk, fl->df_mode == 4};
+  for (int a = 0; a < 10; a++) if (need[a] && !src[a] && n > 0) return fail(IS3D_ERR_ARGUMENT, "a required surface array is NULL");
+
+  SmallArena ar;
+  size_t o_x = 0, o_y = 0, o_c = 0; int nz = 0;
+  if (fl->df_mode == 4) {
+    nz = df->n_jonah;
+    std::vector<double> c(nz);
+    host_spline_init(df->jonah_x, df->jonah_z, nz, c.data());
+    o_x = ar.put(df->jonah_x, nz); o_y = ar.put(df->jonah_z, nz); o_c = ar.put(c.data(), nz);
+  }
+  const int n_blocks_max = (int)((n + 8191) / 8192) + 1;
+  const size_t cell_stride = ((size_t)n * 8 + 255) & ~(size_t)255;
+  CU_CHECK(g_ws.small.reserve(ar.host.size() + 256));
+  CU_CHECK(g_ws.counters.reserve(256));
+  CU_CHECK(g_ws.integ_out.reserve((size_t)n_blocks_max * 24 + 256));
+  if (opt.memory == 0) CU_CHECK(g_ws.raw.reserve(cell_stride * 10 + 256));
+  cudaEvent_t *ev = g_ws.ev;
+  CU_CHECK(cudaEventRecord(ev[0], st));
+  unsigned char *small_d = g_ws.small.as<unsigned char>();
+  if (!ar.host.empty()) CU_CHECK(cudaMemcpyAsync(small_d, ar.host.data(), ar.host.size(), cudaMemcpyHostToDevice, st));
+  const double *dev[10];
+  for (int a = 0; a < 10; a++) {
+    dev[a] = nullptr;
+    if (!need[a] || n == 0) continue;
+    if (opt.memory == 0) {
+      double *d = reinterpret_cast<double *>(g_ws.raw.as<unsigned char>() + cell_stride * a);
+      CU_CHECK(cudaMemcpyAsync(d, src[a], (size_t)n * 8, cudaMemcpyHostToDevice, st));
+      dev[a] = d;
+    } else dev[a] = src[a];
+  }
+  RawCells rc; memset(&rc, 0, sizeof(rc));
+  rc.n = n; rc.tau = dev[0]; rc.ux = dev[1]; rc.uy = dev[2]; rc.un = dev[3]; rc.dat = dev[4]; rc.dax = dev[5]; rc.day = dev[6];
+  rc.dan = dev[7]; rc.bulkPi = dev[8]; rc.P = dev[9];
+  PrepTables tab; memset(&tab, 0, sizeof(tab));
+  if (fl->df_mode == 4) {
+    tab.z.x = reinterpret_cast<const double *>(small_d + o_x); tab.z.y = reinterpret_cast<const double *>(small_d + o_y);
+    tab.z.c = reinterpret_cast<const double *>(small_d + o_c); tab.z.n = nz;
+    tab.bulkPi_over_Peq_max = df->bulkPi_over_Peq_max;
+  }
+  CU_CHECK(cudaMemsetAsync(g_ws.counters.p, 0, sizeof(PrepCounters), st));
+  CU_CHECK(cudaEventRecord(ev[1], st));
+  int n_blocks = 0;
+  CU_CHECK(launch_yield(rc, tab, fl->df_mode, bk ? 1 : 0, g_ws.integ_out.as<double>(), &n_blocks, g_ws.counters.as<PrepCounters>(), st));
+  CU_CHECK(cudaEventRecord(ev[2], st));
+  std::vector<double> part((size_t)n_blocks * 3, 0.0);
+  PrepCounters cnt; memset(&cnt, 0, sizeof(cnt));
+  if (n_blocks) CU_CHECK(cudaMemcpyAsync(part.data(), g_ws.integ_out.p, part.size() * 8, cudaMemcpyDeviceToHost, st));
+  CU_CHECK(cudaMemcpyAsync(&cnt, g_ws.counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+  CU_CHECK(cudaEventRecord(ev[3], st));
+  CU_CHECK(cudaEventSynchronize(ev[3]));
+  double S[3] = {0.0, 0.0, 0.0};
+  for (int b = 0; b < n_blocks; b++) for (int q = 0; q < 3; q++) S[q] += part[(size_t)b * 3 + q];
+  double Neq = 0.0, Nbulk = 0.0;
+  for (int s = 0; s < n_species; s++) { Neq += neq[s]; if (dn_bulk) Nbulk += dn_bulk[s]; }
+  double Ntot = (fl->df_mode == 4) ? S[2] * Neq : S[0] * Neq + S[1] * Nbulk;     // estimate_mean_particle_number, :200-236
+  if (fl->dimension == 2) Ntot *= (2.0 * y_cut);                                  // :822-826
+  *Ntot_out = Ntot;
+  if (stats) {
+    is3d_stats stt; memset(&stt, 0, sizeof(stt));
+    float ms;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]); stt.h2d_ms = ms;
+    cudaEventElapsedTime(&ms, ev[1], ev[2]); stt.kernel_ms = ms;
+    cudaEventElapsedTime(&ms, ev[2], ev[3]); stt.d2h_ms = ms;
+    cudaEventElapsedTime(&ms, ev[0], ev[3]); stt.total_ms = ms;
+    stt.cells_skipped_udsigma = (int64_t)cnt.skipped; stt.gpu_launches = n_blocks ? 1 : 0;
+    stt.evaluations = n * (int64_t)n_species;
+    *stats = stt;
+  }
+  if (cnt.range_error) return fail(IS3D_ERR_TABLE_RANGE, "a cell's Pi/P lies outside the Jonah z table");
+  return IS3D_OK;
+}
+

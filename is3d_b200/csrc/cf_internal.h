@@ -96,6 +96,9 @@ cudaError_t launch_hot(int model, const HotParams &hp, int variant, cudaStream_t
 cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, int64_t n_active, double *out, cudaStream_t st);
 // integ -> out[unit][species], unit = chunk (mode 1) or slot (mode 2, summed over chunks)
 cudaError_t launch_integ_reduce(const HotParams &hp, int n_units, double *out, cudaStream_t st);
+// sampler mean yield: per-block triples (sum u.dsigma, sum u.dsigma Pi, sum u.dsigma z) in partial[3 * n_blocks]
+cudaError_t launch_yield(const RawCells &cells, const PrepTables &tab, int df_mode, int include_bulk, double *partial, int *n_blocks,
+                         PrepCounters *counters, cudaStream_t st);
 cudaError_t launch_fp64_peak(double *sink, int iters, cudaStream_t st, int *blocks, int *threads, long long *dfma_per_thread);
 void hot_variant_shape(int variant, int dim2, int *nyt, int *npt, int *ct, int *max_warps);
 

@@ -643,4 +643,57 @@ cudaError_t launch_prepare_vh(const is3d_flags &fl, const RawCells &cells, const
   return cudaGetLastError();
 }
 
+// =====================================================================================================================
+// Sampler mean yield: EmissionFunctionArray::calculate_total_yield, emissionfunction_sampling_kernels.cpp
+// :653-831.  Without baryon diffusion the species sum factorises, sum_s [u.dsigma (n_eq,s + Pi dn_bulk,s)] (df_mode 1-3) or
+// u.dsigma z(Pi/P) n_eq,s (df_mode 4), so the device only reduces three per-cell quantities over the surface:
+//   S0 = sum u.dsigma,  S1 = sum u.dsigma Pi,  S2 = sum u.dsigma z(Pi/P),  cells with u.dsigma <= 0 skipped (:690).
+// Deterministic: block b owns cells [b * kYieldSpan, (b + 1) * kYieldSpan), threads stride through them, fixed-order tree in
+// shared memory, one triple per block; the host adds the triples in block order.
+constexpr int kYieldThreads = 256, kYieldSpan = 8192;
+__global__ void __launch_bounds__(kYieldThreads)
+yield_kernel(RawCells cells, PrepTables tab, int df_mode, int include_bulk, double *__restrict__ partial, PrepCounters *counters)
+{
+  __shared__ double red[3][kYieldThreads];
+  const int64_t lo = (int64_t)blockIdx.x * kYieldSpan, hi = min(lo + (int64_t)kYieldSpan, cells.n);
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  unsigned long long skipped = 0, bad_cells = 0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += kYieldThreads) {
+    const double tau = cells.tau[i], tau2 = tau * tau;
+    const double ux = cells.ux[i], uy = cells.uy[i], un = cells.un[i];
+    const double ut = sqrt(1.0 + ux * ux + uy * uy + tau2 * un * un);
+    const double udsigma = ut * cells.dat[i] + ux * cells.dax[i] + uy * cells.day[i] + un * cells.dan[i];
+    if (udsigma <= 0.0) { skipped++; continue; }
+    double bulkPi = include_bulk ? cells.bulkPi[i] : 0.0;
+    double z = 0.0;
+    if (df_mode == 4) {
+      const double Pr = cells.P[i], mx = tab.bulkPi_over_Peq_max;
+      if (bulkPi <= -Pr) bulkPi = -(1.0 - 1.e-5) * Pr;                    // :753-754
+      else if (bulkPi / Pr >= mx) bulkPi = Pr * (mx - 1.e-5);
+      bool bad = false;
+      z = spline_eval(tab.z, bulkPi / Pr, bad);
+      if (bad) { bad_cells++; continue; }
+    }
+    s0 += udsigma; s1 += udsigma * bulkPi; s2 += udsigma * z;
+  }
+  red[0][threadIdx.x] = s0; red[1][threadIdx.x] = s1; red[2][threadIdx.x] = s2;
+  __syncthreads();
+  for (int w = kYieldThreads / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) for (int q = 0; q < 3; q++) red[q][threadIdx.x] += red[q][threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) for (int q = 0; q < 3; q++) partial[(int64_t)blockIdx.x * 3 + q] = red[q][0];
+  if (skipped) atomicAdd(&counters->skipped, skipped);
+  if (bad_cells) atomicAdd(&counters->range_error, bad_cells);
+}
+
+cudaError_t launch_yield(const RawCells &cells, const PrepTables &tab, int df_mode, int include_bulk, double *partial, int *n_blocks,
+                         PrepCounters *counters, cudaStream_t st)
+{
+  *n_blocks = (int)((cells.n + kYieldSpan - 1) / kYieldSpan);
+  if (*n_blocks == 0) return cudaSuccess;
+  yield_kernel<<<(unsigned)*n_blocks, kYieldThreads, 0, st>>>(cells, tab, df_mode, include_bulk, partial, counters);
+  return cudaGetLastError();
+}
+
 }  // namespace is3d

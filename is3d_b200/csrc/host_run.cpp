@@ -8,6 +8,7 @@
 // including append mode and the requirement that results/ already exists.
 #include "../../include/is3d_b200.h"
 #include "host_io.h"
+#include "host_math.h"
 #include <cmath>
 #include <complex>
 #include <cstdio>
@@ -482,6 +483,77 @@ extern "C" int is3d_b200_jonah_tables(int32_t n_particles, const double *mass, c
   std::memcpy(lambda2_301, t.jonah_lambda2.data(), 301 * sizeof(double));
   std::memcpy(z301, t.jonah_z.data(), 301 * sizeof(double));
   if (mx) *mx = t.bulkPi_over_Peq_max;
+  return IS3D_OK;
+}
+
+// Per-species equilibrium density and bulk / diffusion corrections at the surface-average T, E, P: what
+// Deltaf_Data::compute_particle_densities (deltafReader.cpp:536-650) stores in particle_info and the sampler's yield
+// estimate consumes.  avg5 = (T, E, P, muB, nB) as is3d_b200_surface_averages returns them; include_baryon = 0 (muB = nB = 0).
+extern "C" int is3d_b200_particle_densities(int32_t n, const double *mass, const double *degeneracy, const double *baryon,
+                                            const double *sign, const double *avg5, int32_t df_mode, const is3d_df_tables *df,
+                                            int32_t n_points, const double *root1, const double *weight1, const double *root2,
+                                            const double *weight2, const double *root3, const double *weight3,
+                                            double *neq_out, double *dn_bulk_out, double *dn_diff_out)
+{
+  if (n <= 0 || !mass || !degeneracy || !baryon || !sign || !avg5 || !df || n_points <= 0 || !root1 || !weight1 || !neq_out || !dn_bulk_out || !dn_diff_out)
+    return IS3D_ERR_ARGUMENT;
+  if (df_mode < 1 || df_mode > 4) return IS3D_ERR_ARGUMENT;
+  if ((df_mode == 1 && (!root2 || !weight2 || !root3 || !weight3 || !df->c0 || !df->c2)) ||
+      ((df_mode == 2 || df_mode == 3) && (!root2 || !weight2 || !df->F || !df->betabulk))) return IS3D_ERR_ARGUMENT;
+  const double hbarC = 0.197327053, two_pi2_hbarC3 = 2.0 * std::pow(M_PI, 2) * std::pow(hbarC, 3);
+  const double T = avg5[0], E = avg5[1], P = avg5[2], muB = avg5[3], nB = avg5[4];
+  // Deltaf_Data::cubic_spline at (T, bulkPi = 0), deltafReader.cpp:325-395: T-scalings undone, G = c1 = c3 = c4 = 0, betaV = 1
+  auto coef = [&](const double *y, double *out) {
+    if (!y || df->n_T < 3) return false;
+    std::vector<double> c(df->n_T);
+    host_spline_init(df->T, y, df->n_T, c.data());
+    return host_spline_eval(df->T, y, c.data(), df->n_T, T, out);
+  };
+  const double T4 = T * T * T * T;
+  double c0 = 0, c2 = 0, F = 0, betabulk = 1;
+  if (df_mode == 1) {
+    if (!coef(df->c0, &c0) || !coef(df->c2, &c2)) { g_host_error = "average temperature outside the delta-f coefficient table"; return IS3D_ERR_TABLE_RANGE; }
+    c0 /= T4; c2 /= T4;
+  } else if (df_mode == 2 || df_mode == 3) {
+    if (!coef(df->F, &F) || !coef(df->betabulk, &betabulk)) { g_host_error = "average temperature outside the delta-f coefficient table"; return IS3D_ERR_TABLE_RANGE; }
+    F *= T; betabulk *= T4;
+  }
+  const double c1 = 0.0, c3 = 0.0, c4 = 0.0, G = 0.0, betaV = 1.0;
+  const double alphaB = muB / T, baryon_enthalpy_ratio = nB / (E + P);
+  auto sum = [&](double (*f)(double, double, double, double, double), const double *root, const double *w, double mbar, double b, double sg) {
+    double acc = 0.0;
+    for (int k = 0; k < n_points; k++) acc += w[k] * f(root[k], mbar, alphaB, b, sg);
+    return acc;
+  };
+  // integrands of gaussThermal.cpp:19-90
+  auto neq_i = [](double p, double m, double a, double b, double s) { const double Eb = std::sqrt(p * p + m * m); return p * std::exp(p) / (std::exp(Eb - b * a) + s); };
+  auto J10_i = [](double p, double m, double a, double b, double s) { const double Eb = std::sqrt(p * p + m * m), q = std::exp(Eb - b * a) + s; return p * std::exp(p + Eb - b * a) / (q * q); };
+  auto J11_i = [](double p, double m, double a, double b, double s) { const double Eb = std::sqrt(p * p + m * m), q = std::exp(Eb - b * a) + s; return p * p * p / (Eb * Eb) * std::exp(p + Eb - b * a) / (q * q); };
+  auto J20_i = [](double p, double m, double a, double b, double s) { const double Eb = std::sqrt(p * p + m * m), q = std::exp(Eb - b * a) + s; return Eb * std::exp(p + Eb - b * a) / (q * q); };
+  auto J30_i = [](double p, double m, double a, double b, double s) { const double Eb = std::sqrt(p * p + m * m), q = std::exp(Eb - b * a) + s; return Eb * Eb / p * std::exp(p + Eb - b * a) / (q * q); };
+  auto J31_i = [](double p, double m, double a, double b, double s) { const double Eb = std::sqrt(p * p + m * m), q = std::exp(Eb - b * a) + s; return p * std::exp(p + Eb - b * a) / (q * q); };
+  for (int i = 0; i < n; i++) {
+    const double m = mass[i], g = degeneracy[i], b = baryon[i], sg = sign[i], mbar = m / T;
+    const double neq_fact = g * std::pow(T, 3) / two_pi2_hbarC3;
+    const double neq = neq_fact * sum(neq_i, root1, weight1, mbar, b, sg);
+    double dn_bulk = 0.0, dn_diff = 0.0;
+    if (df_mode == 1) {
+      const double J10_fact = g * std::pow(T, 3) / two_pi2_hbarC3, J20_fact = g * std::pow(T, 4) / two_pi2_hbarC3;
+      const double J30_fact = g * std::pow(T, 5) / two_pi2_hbarC3, J31_fact = g * std::pow(T, 5) / two_pi2_hbarC3 / 3.0;
+      const double J10 = J10_fact * sum(J10_i, root1, weight1, mbar, b, sg), J20 = J20_fact * sum(J20_i, root2, weight2, mbar, b, sg);
+      const double J30 = J30_fact * sum(J30_i, root3, weight3, mbar, b, sg), J31 = J31_fact * sum(J31_i, root3, weight3, mbar, b, sg);
+      dn_bulk = ((c0 - c2) * m * m * J10 + c1 * b * J20 + (4.0 * c2 - c0) * J30);
+      dn_diff = b * c3 * neq * T + c4 * J31;
+    } else if (df_mode == 2 || df_mode == 3) {
+      const double J10_fact = g * std::pow(T, 3) / two_pi2_hbarC3, J11_fact = g * std::pow(T, 3) / two_pi2_hbarC3 / 3.0;
+      const double J20_fact = g * std::pow(T, 4) / two_pi2_hbarC3;
+      const double J10 = J10_fact * sum(J10_i, root1, weight1, mbar, b, sg), J11 = J11_fact * sum(J11_i, root1, weight1, mbar, b, sg);
+      const double J20 = J20_fact * sum(J20_i, root2, weight2, mbar, b, sg);
+      dn_bulk = (neq + (b * J10 * G) + (J20 * F / std::pow(T, 2))) / betabulk;
+      dn_diff = (neq * T * baryon_enthalpy_ratio - b * J11) / betaV;
+    }
+    neq_out[i] = neq; dn_bulk_out[i] = dn_bulk; dn_diff_out[i] = dn_diff;
+  }
   return IS3D_OK;
 }
 

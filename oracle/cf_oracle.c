@@ -741,6 +741,94 @@ int64_t cfo_spacetime_feqmod(const cfo_flags *fl, const cfo_cells *c, const cfo_
   return feqmod_core(fl, c, sp, g, tab, gla, NULL, breakdown_out, spec, dN_tau, dN_r, dN_taur, dN_dydeta, dN_dy);
 }
 
+/* ---------------------------------------------------------------- N4: sampler mean yield */
+static double J11_int(double pbar, double mbar, double alphaB, double baryon, double sign)
+{ double Ebar = sqrt(pbar * pbar + mbar * mbar); double q = exp(Ebar - baryon * alphaB) + sign;
+  return pbar * pbar * pbar / (Ebar * Ebar) * exp(pbar + Ebar - baryon * alphaB) / (q * q); }
+static double J30_int(double pbar, double mbar, double alphaB, double baryon, double sign)
+{ double Ebar = sqrt(pbar * pbar + mbar * mbar); double q = exp(Ebar - baryon * alphaB) + sign;
+  return Ebar * Ebar / pbar * exp(pbar + Ebar - baryon * alphaB) / (q * q); }
+static double J31_int(double pbar, double mbar, double alphaB, double baryon, double sign)
+{ double Ebar = sqrt(pbar * pbar + mbar * mbar); double q = exp(Ebar - baryon * alphaB) + sign;
+  return pbar * exp(pbar + Ebar - baryon * alphaB) / (q * q); }
+
+/* Deltaf_Data::compute_particle_densities, deltafReader.cpp:536-650: densities at the surface-average T, E, P (avg5 = T, E, P,
+ * muB, nB; muB = nB = 0 here).  root3 / weight3 are the alpha = 3 Gauss-Laguerre nodes (df_mode 1 only). */
+int cfo_particle_densities(int n, const double *mass, const double *degeneracy, const double *baryon, const double *sign,
+                           const double *avg5, int df_mode, const cfo_df_tables *tab, const cfo_laguerre *gla,
+                           const double *root3, const double *weight3, double *neq_out, double *bulk_out, double *diff_out)
+{
+  const double two_pi2_hbarC3 = 2.0 * pow(M_PI, 2) * pow(hbarC, 3);
+  const double T = avg5[0], E = avg5[1], P = avg5[2], muB = avg5[3], nB = avg5[4];
+  cfo_dfcoef df;
+  if (cfo_df_coefficients(tab, df_mode, T, E, P, 0.0, &df)) return -3;
+  const double alphaB = muB / T, baryon_enthalpy_ratio = nB / (E + P);
+  const int pts = gla->n_points;
+  for (int i = 0; i < n; i++) {
+    const double m = mass[i], g = degeneracy[i], b = baryon[i], sg = sign[i], mbar = m / T;
+    const double neq_fact = g * pow(T, 3) / two_pi2_hbarC3;
+    const double neq = neq_fact * gauss_thermal(neq_int, gla->root1, gla->weight1, pts, mbar, alphaB, b, sg);
+    double dn_bulk = 0.0, dn_diff = 0.0;
+    if (df_mode == 1) {
+      const double J10_fact = g * pow(T, 3) / two_pi2_hbarC3, J20_fact = g * pow(T, 4) / two_pi2_hbarC3;
+      const double J30_fact = g * pow(T, 5) / two_pi2_hbarC3, J31_fact = g * pow(T, 5) / two_pi2_hbarC3 / 3.0;
+      const double J10 = J10_fact * gauss_thermal(J10_int, gla->root1, gla->weight1, pts, mbar, alphaB, b, sg);
+      const double J20 = J20_fact * gauss_thermal(J20_int, gla->root2, gla->weight2, pts, mbar, alphaB, b, sg);
+      const double J30 = J30_fact * gauss_thermal(J30_int, root3, weight3, pts, mbar, alphaB, b, sg);
+      const double J31 = J31_fact * gauss_thermal(J31_int, root3, weight3, pts, mbar, alphaB, b, sg);
+      dn_bulk = ((df.c0 - df.c2) * m * m * J10 + df.c1 * b * J20 + (4.0 * df.c2 - df.c0) * J30);
+      dn_diff = b * df.c3 * neq * T + df.c4 * J31;
+    } else if (df_mode == 2 || df_mode == 3) {
+      const double J10_fact = g * pow(T, 3) / two_pi2_hbarC3, J11_fact = g * pow(T, 3) / two_pi2_hbarC3 / 3.0;
+      const double J20_fact = g * pow(T, 4) / two_pi2_hbarC3;
+      const double J10 = J10_fact * gauss_thermal(J10_int, gla->root1, gla->weight1, pts, mbar, alphaB, b, sg);
+      const double J11 = J11_fact * gauss_thermal(J11_int, gla->root1, gla->weight1, pts, mbar, alphaB, b, sg);
+      const double J20 = J20_fact * gauss_thermal(J20_int, gla->root2, gla->weight2, pts, mbar, alphaB, b, sg);
+      dn_bulk = (neq + (b * J10 * df.G) + (J20 * df.F / pow(T, 2))) / df.betabulk;
+      dn_diff = (neq * T * baryon_enthalpy_ratio - b * J11) / df.betaV;
+    }
+    neq_out[i] = neq; bulk_out[i] = dn_bulk; diff_out[i] = dn_diff;
+  }
+  return 0;
+}
+
+/* EmissionFunctionArray::calculate_total_yield, emissionfunction_sampling_kernels.cpp:653-831, without baryon diffusion
+ * (V.dsigma = 0, so the reference's uninitialised ds_space never contributes): per cell and species
+ *   df_mode 1-3: u.dsigma (n_eq + Pi dn_bulk);   df_mode 4: u.dsigma z(Pi/P) n_eq  (does_feqmod_breakdown is false for Jonah).
+ * Returns the skipped-cell count, *Ntot gets the yield (times 2 y_cut in 2+1D). */
+int64_t cfo_total_yield(const cfo_flags *fl, const cfo_cells *c, int n_species, const double *neq, const double *bulk,
+                        const cfo_df_tables *tab, double y_cut, double *Ntot_out)
+{
+  spline_cache sc; cache_build(&sc, tab);
+  double Ntot = 0.0; int64_t skipped = 0; int bad = 0;
+  for (int64_t i = 0; i < c->n_cells; i++) {
+    const double tau = c->tau[i], tau2 = tau * tau;
+    const double ux = c->ux[i], uy = c->uy[i], un = c->un[i];
+    const double ut = sqrt(1.0 + ux * ux + uy * uy + tau2 * un * un);
+    const double udsigma = ut * c->dat[i] + ux * c->dax[i] + uy * c->day[i] + un * c->dan[i];
+    if (udsigma <= 0.0) { skipped++; continue; }
+    double bulkPi = fl->include_bulk ? c->bulkPi[i] : 0.0;
+    const double P = c->P[i];
+    cfo_dfcoef df; memset(&df, 0, sizeof(df));
+    if (fl->df_mode == 4) {
+      const double mx = tab->bulkPi_over_Peq_max;
+      if (bulkPi <= -P) bulkPi = -(1.0 - 1.e-5) * P;
+      else if (bulkPi / P >= mx) bulkPi = P * (mx - 1.e-5);
+    }
+    if (df_eval(&sc, fl->df_mode, c->T[i], c->E[i], P, bulkPi, &df)) bad = 1;
+    const double ds_time = udsigma;                   /* Surface_Element_Vector::boost_dsigma_to_lrf, viscous_correction.cpp:76 */
+    for (int s = 0; s < n_species; s++) {
+      if (fl->df_mode == 4) Ntot += ds_time * df.z * neq[s];
+      else Ntot += ds_time * (neq[s] + bulkPi * bulk[s]);
+    }
+  }
+  cache_free(&sc);
+  if (bad) return -3;
+  if (fl->dimension == 2) Ntot *= (2.0 * y_cut);
+  *Ntot_out = Ntot;
+  return skipped;
+}
+
 /* ---------------------------------------------------------------- a3: anisotropic PL-matching kernel, :2140-2393 */
 int64_t cfo_smooth_vah(const cfo_flags *fl, const cfo_cells *c, const cfo_species *sp, const cfo_grid *g, double *dN)
 {

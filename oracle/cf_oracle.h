@@ -114,6 +114,14 @@ int64_t cfo_spacetime_feqmod(const cfo_flags *fl, const cfo_cells *c, const cfo_
                              const cfo_df_tables *tab, const cfo_laguerre *gla, const cfo_spacetime_spec *spec,
                              double *dN_tau, double *dN_r, double *dN_taur, double *dN_dydeta, double *dN_dy, int64_t *breakdown);
 
+/* Sampler mean yield: Deltaf_Data::compute_particle_densities (deltafReader.cpp:536-650) and
+ * EmissionFunctionArray::calculate_total_yield (emissionfunction_sampling_kernels.cpp:653-831), include_baryon = 0. */
+int cfo_particle_densities(int n, const double *mass, const double *degeneracy, const double *baryon, const double *sign,
+                           const double *avg5, int df_mode, const cfo_df_tables *tab, const cfo_laguerre *gla,
+                           const double *root3, const double *weight3, double *neq_out, double *bulk_out, double *diff_out);
+int64_t cfo_total_yield(const cfo_flags *fl, const cfo_cells *c, int n_species, const double *neq, const double *bulk,
+                        const cfo_df_tables *tab, double y_cut, double *Ntot_out);
+
 /* VAH helpers: aL_fit / R200 (arsenal.cpp:999-1066) and the (Lambda, aL) bilinear lookup of
  * src/cuda/deltafReader.cu:192-277 */
 double cfo_aL_fit(double pl_over_peq);

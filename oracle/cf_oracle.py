@@ -69,6 +69,7 @@ def lib():
         L.cfo_smooth_vah.restype = C.c_int64
         L.cfo_spacetime_vh.restype = C.c_int64
         L.cfo_spacetime_feqmod.restype = C.c_int64
+        L.cfo_total_yield.restype = C.c_int64
         L.cfo_jonah_tables.restype = C.c_double
         L.cfo_aL_fit.restype = C.c_double; L.cfo_aL_fit.argtypes = [C.c_double]
         L.cfo_R200.restype = C.c_double; L.cfo_R200.argtypes = [C.c_double]
@@ -228,6 +229,31 @@ def read_spacetime_files(workdir, mcid, bins, eta_pts):
                dN_taur=(c[:, 2].reshape(nr, nt) * (2.0 * np.pi * tw * rw) * r_mid[:, None] * tau_mid[None, :]).T,
                dN_dydeta=e[:, 1], eta_column=e[:, 0], tau_mid=a[:, 0], r_mid=b[:, 0])
     return out
+
+
+def particle_densities(species, avg5, df_mode, tables, gla, root3, weight3):
+    """(n_eq, dn_bulk, dn_diff) per species at the surface averages avg5 = (T, E, P, muB, nB)"""
+    keep = _Keep()
+    n = len(species["mass"])
+    neq = np.zeros(n); bulk = np.zeros(n); diff = np.zeros(n)
+    t = _tables(keep, tables); la = _laguerre(keep, gla)
+    rc = lib().cfo_particle_densities(C.c_int(n), keep.arr(species["mass"]), keep.arr(species["degeneracy"]), keep.arr(species["baryon"]),
+                                      keep.arr(species["sign"]), keep.arr(avg5), C.c_int(df_mode), C.byref(t), C.byref(la),
+                                      keep.arr(root3), keep.arr(weight3), _p(neq), _p(bulk), _p(diff))
+    if rc:
+        raise RuntimeError("cf_oracle error %d" % rc)
+    return neq, bulk, diff
+
+
+def total_yield(flags, cells, neq, bulk, tables, y_cut):
+    """sampler mean yield; returns (Ntot, skipped cells)"""
+    keep = _Keep()
+    fl = _flags(flags); c = _cells(keep, cells); t = _tables(keep, tables)
+    out = C.c_double(0.0)
+    rc = lib().cfo_total_yield(C.byref(fl), C.byref(c), C.c_int(len(neq)), keep.arr(neq), keep.arr(bulk), C.byref(t), C.c_double(y_cut), C.byref(out))
+    if rc < 0:
+        raise RuntimeError("cf_oracle error %d" % rc)
+    return out.value, int(rc)
 
 
 # --------------------------------------------------------------------------- compiled reference (oracle/_ref)

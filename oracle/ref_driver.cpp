@@ -17,6 +17,7 @@
 // usage (run inside a directory laid out like an iS3D checkout):
 //   is3d_ref kernel  [out.bin]   hot-path call only, raw dump + timing to stdout as a JSON line
 //   is3d_ref full    [out.bin]   calculate_spectra() incl. the reference's text writers, then raw dump
+//   is3d_ref yield   [out.bin]   sampler mean yield: calculate_total_yield() with the reference's own species densities
 //   is3d_ref vah     [out.bin]   mode-2 surface + input/vah_coefficients.bin (c0..c4 per cell) -> VAH_PL kernel
 #include <iostream>
 #include <sstream>
@@ -130,7 +131,25 @@ int main(int argc, char **argv)
     Gauss_Laguerre *gla = new Gauss_Laguerre;
     gla->load_roots_and_weights("tables/gla_roots_weights_32_points.txt");
 
-    if (what == "vah")
+    if (what == "yield")
+    {
+      // sampler mean yield: the densities come from compute_particle_densities (called above), emissionfunction.cpp:1296-1306
+      double *Eq = zeros(npart), *Bk = zeros(npart), *Df = zeros(npart);
+      for (int ipart = 0; ipart < npart; ipart++)
+      {
+        particle_info *p = &particle_data[efa.chosen_particles_sampling_table[ipart]];
+        Eq[ipart] = p->equilibrium_density;  Bk[ipart] = p->bulk_density;  Df[ipart] = p->diff_density;
+      }
+      auto t0 = chrono::steady_clock::now();
+      double Ntot = efa.calculate_total_yield(Eq, Bk, Df, T, P, E, tau, ux, uy, un, dat, dax, day, dan, pixx, pixy, pixn, piyy, piyn,
+                                              bulkPi, muB, nB, Vx, Vy, Vn, df_data, gla);
+      seconds = chrono::duration<double>(chrono::steady_clock::now() - t0).count();
+      printf("\nREF_YIELD %.17g\n", Ntot);
+      printf("REF_DENSITIES");
+      for (int ipart = 0; ipart < npart; ipart++) printf(" %.17g %.17g", Eq[ipart], Bk[ipart]);
+      printf("\n");
+    }
+    else if (what == "vah")
     {
       FILE *f = fopen("input/vah_coefficients.bin", "rb");
       if (!f) { fprintf(stderr, "ref_driver: input/vah_coefficients.bin missing\n"); return 2; }
