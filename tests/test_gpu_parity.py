@@ -308,3 +308,20 @@ def test_full_size_cfg3_properties(fx):
         assert np.array_equal(o == 0.0, w == 0.0)
         nz = w != 0.0
         assert np.max(np.abs(o[nz] - w[nz]) / w[nz]) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------- every compiled tile variant
+@pytest.mark.parametrize("name", ["s3_df1", "s3_df2", "s3stress_df3", "s3_df4", "s2_df1", "s2_df3", "vah_3d", "s2_ideal"])
+def test_every_tile_variant(name, fx):
+    """all 16 register-tile variants (is3d_options.tile_variant) of every model give the golden spectra"""
+    from common import vah_problem
+    gold = load_golden(name)
+    if name.startswith("vah"):
+        fl, cells, sp, g, _ = vah_problem(gold["recipe"], fx); tab = gla = None
+    else:
+        fl, cells, sp, g, tab, gla = problem_from_recipe(gold["recipe"], fx)
+    for variant in range(1, 17):
+        dN, st = api.smooth_spectra(fl, cells, sp, g, tab, gla, tile_variant=variant)
+        assert st["tile_variant"] == variant - 1
+        rep = compare(dN, gold["dN"])
+        assert rep["ok"], (name, variant, rep)

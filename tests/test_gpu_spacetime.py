@@ -184,3 +184,20 @@ def test_spacetime_rejects_what_the_reference_cannot_do(fx):
         api.spacetime_distributions(dict(fl, mode=2), cells, sp, g, tab, gla, BINS)                 # no anisotropic dN_dX routine
     with pytest.raises(api.Is3dError):
         api.spacetime_distributions(fl, cells, sp, g, tab, gla, dict(BINS, tau_bins=0))
+
+
+@pytest.mark.parametrize("dimension,df_mode", [(3, 1), (3, 3), (2, 2), (2, 4)])
+def test_spacetime_nonstandard_grids(fx, dimension, df_mode):
+    """table lengths that do not line up with warps or register tiles: 13 pT points (a warp spans several species, a species
+    spans two warps), 5 phi points, 9 y points, 37 eta points; 11 species"""
+    fl, cells, sp, g0, tab, gla = problem(fx, 120 if dimension == 3 else 24, dimension, df_mode, 9800 + df_mode,
+                                          chosen=fx["chosen_urqmd"][:11])
+    g = dict(g0)
+    g["pT"] = g0["pT"][:13]; g["pT_weight"] = g0["pT_weight"][:13]
+    g["phi"] = g0["phi"][:5]; g["phi_weight"] = g0["phi_weight"][:5]
+    g["y"] = g0["y"][3:12]; g["eta"] = g0["eta"][100:137]; g["eta_weight"] = g0["eta_weight"][100:137]
+    ref, skipped = cfo.spacetime(fl, cells, sp, g, tab, BINS, gla)
+    for variant in (0, 1, 4):
+        got, st = api.spacetime_distributions(fl, cells, sp, g, tab, gla, BINS, tile_variant=variant)
+        assert st["cells_skipped_udsigma"] == skipped
+        check(got, ref)
