@@ -365,7 +365,10 @@ def main():
                 "peak_source": "measured live: dependency-free DFMA chains on all SMs, %.1f s sustained (burst %.2f TFLOP/s); "
                                "MEASURED_PEAKS.json has no FP64 entry" % (2.0, peak_burst),
                 "hbm": {"record_bytes_per_launch": int(rec_bytes), "note": "records are re-read by every bin-tile column from L2/HBM; "
-                        "see profiles/ for dram__bytes of the ncu capture", "hbm_peak_gbs": _measured_hbm()}}
+                        "ncu capture of a 20 000-cell launch (profiles/r1_ncu_full_cf_kernel_lin14_v3.json): 67 MB DRAM read + 273 MB written "
+                        "in 169 ms = 2 GB/s, i.e. the path is not HBM-bound", "hbm_peak_gbs": _measured_hbm()},
+                "reading": "W is the reference's flop count per evaluation as written (SURVEY 8d); the restructured kernel executes ~18 FP64 "
+                           "instructions per evaluation, so frac can exceed 1 -- the FP64 pipe itself is 56 % busy in the ncu capture"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
