@@ -26,5 +26,12 @@ np.save(os.path.join(out, "dN_%d.npy" % rank), dN.cpu().numpy())
 if rank == 0:
     single, _ = api.smooth_spectra(fl, dev, sp, g, tab, None, memory="device")
     np.save(os.path.join(out, "dN_single.npy"), single.cpu().numpy())
+# operation = 0: the histograms are sums over cells, one all-reduce of the concatenated raw sums
+bins = dict(tau_min=0.0, tau_max=12.0, tau_bins=24, r_min=0.0, r_max=12.0, r_bins=12)
+res, _ = distributed.spacetime_distributions_sharded(fl, dev, sp, g, tab, None, bins, memory="device")
+np.savez(os.path.join(out, "st_%d.npz" % rank), **res)
+if rank == 0:
+    single, _ = api.spacetime_distributions(fl, dev, sp, g, tab, None, bins, memory="device")
+    np.savez(os.path.join(out, "st_single.npz"), **single)
 dist.barrier()
 dist.destroy_process_group()

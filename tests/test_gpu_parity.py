@@ -258,6 +258,11 @@ def test_two_gpu_nccl(fx, tmp_path):
     d0 = np.load(tmp_path / "dN_0.npy"); ref = np.load(tmp_path / "dN_single.npy")
     nz = ref != 0
     assert np.max(np.abs(d0[nz] - ref[nz]) / ref[nz]) < 1e-12 and np.all(d0[~nz] == 0)
+    s0 = np.load(tmp_path / "st_0.npz"); s1 = np.load(tmp_path / "st_1.npz"); ss = np.load(tmp_path / "st_single.npz")
+    for k in ("dN_tau", "dN_r", "dN_taur", "dN_dydeta", "dN_dy"):
+        assert np.array_equal(s0[k], s1[k])
+        assert np.array_equal(s0[k] == 0, ss[k] == 0)
+        assert np.abs(s0[k] - ss[k]).max() <= 1e-12 * np.abs(ss[k]).max()
 
 
 def test_in_memory_surface_entry(fx):
