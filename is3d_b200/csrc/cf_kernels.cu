@@ -45,11 +45,14 @@ __device__ __forceinline__ double distribution(double x, double s, double K2, do
   return fma(feq, df, feq);
 }
 
-// SB: evaluations are grouped SB slots x NPT phi points per divergent region (0: one region per evaluation).  Grouping
-// lets the scheduler interleave the independent exp / reciprocal chains of the group (ILP); the cost is that a group is
-// evaluated as soon as one of its members is alive (see group_flags() in cf_device.cuh for how dead members end up as 0).
-// e^{-x[i]} for a group of N arguments, staged so that the N polynomial chains interleave and the slow branch (sub-normal
-// results, dead members) is taken once per group
+// SB selects how the NPT evaluations of a (cell, slot) are scheduled:
+//   0  one divergent region per evaluation (distribution());
+//   1  the NPT evaluations form one staged group (distribution_group()): their exp / reciprocal chains interleave (ILP); the
+//      price is that a group is evaluated as soon as one member is alive (group_flags() in cf_device.cuh: how dead members
+//      end up contributing an exact 0);
+//   3  like 1 with e^{-x} = e^{-mT Ax} e^{+pT Bx} factored into one exponential per slot and one per phi point (2+1D default);
+//   4  like 1 with the classification of slot j + 1 issued before slot j is evaluated (3+1D default).
+// exp_neg_group: e^{-x[i]} for a group of N arguments, the slow branch (sub-normal results, dead members) taken once per group
 template <int N>
 __device__ __forceinline__ void exp_neg_group(const double (&x)[N], bool maybe_rare, double (&a)[N])
 {
@@ -427,29 +430,6 @@ cf_kernel(const HotParams hp)
           }
         }
       };
-      // two slots x NPT phi points per region (linear models, 3+1D)
-      auto slot_pair = [&](int j, double *accj) {
-        const double2 *y0 = reinterpret_cast<const double2 *>(Ys + (c * nst + j) * RY);
-        const double2 *y1 = y0 + RY / 2;
-        const double2 a0 = y0[0], a1 = y0[1], a2 = y0[2], b0 = y1[0], b1 = y1[1], b2 = y1[2];
-        const double aA = mT * a0.x, cA = mT * a0.y, h0A = mT2 * a1.x, h1A = mT * a1.y, h2A = mT * a2.x, wA = a2.y;
-        const double aB = mT * b0.x, cB = mT * b0.y, h0B = mT2 * b1.x, h1B = mT * b1.y, h2B = mT * b2.x, wB = b2.y;
-        double xv[2 * NPT]; bool any, rare, dilute;
-#pragma unroll
-        for (int k = 0; k < NPT; k++) { xv[k] = aA - q[k]; xv[NPT + k] = aB - q[k]; }
-        group_flags<2 * NPT>(xv, any, rare, dilute);
-        if (any) {
-          double sv[2 * NPT], pv[2 * NPT], fv[2 * NPT];
-#pragma unroll
-          for (int k = 0; k < NPT; k++) {
-            pv[k] = fma(wA, pd[k], cA); pv[NPT + k] = fma(wB, pd[k], cB);
-            sv[k] = sterm(j, k, h0A, h1A, h2A); sv[NPT + k] = sterm(j + 1, k, h0B, h1B, h2B);
-          }
-          distribution_group<MODEL, 2 * NPT>(xv, rare, dilute, sv, K2, K3, sign, reg_thr, one_hi, fv);
-#pragma unroll
-          for (int k = 0; k < 2 * NPT; k++) accumulate_pos(accj[k], pv[k], fv[k], thr_hi);
-        }
-      };
       // SB == 4 (linear models, 3+1D): like SB == 1, but the aliveness test of slot j + 1 is issued before slot j is
       // evaluated, so that the skip branch of the next slot never waits for its predicate chain (DMUL, DADD, 2 ISETP)
       auto probe = [&](int j, double (&x)[NPT], bool &any, bool &rare, bool &dilute) {
@@ -486,10 +466,6 @@ cf_kernel(const HotParams hp)
           for (int k = 0; k < NPT; k++) xa[k] = xb[k];
           anya = anyb; rarea = rareb; dila = dilb;
         }
-      } else if (SB == 2 && MODEL != M_FEQMOD && MODEL != M_VAH) {
-#pragma unroll
-        for (int j = 0; j + 1 < NYT; j += 2) slot_pair(j, acc + j * NPT);
-        if (NYT & 1) slot(NYT - 1, acc + (NYT - 1) * NPT);
       } else {
 #pragma unroll
         for (int j = 0; j < NYT; j++) slot(j, acc + j * NPT);
@@ -612,8 +588,8 @@ cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, i
 
 // ------------------------------------------------------------------------------------------------ dispatch
 // Register-tile variants: (slots per tile, phi points per tile, cells per TMA tile, min blocks per SM, grouping SB).
-// Variant 0 is the default; the others exist for tuning (is3d_options.tile_variant, bench.py --variant).
-// Variants >= 8 are compiled for the 14-moment model only (tuning sweep) and fall back to variant 0 elsewhere.
+// is3d_options.tile_variant = k selects entry k - 1 (0 = the tuned default of the model, chosen in cf_api.cu); every entry is
+// compiled for every model and covered by tests/test_gpu_parity.py::test_every_tile_variant.  minb >= 7 means 2-warp blocks.
 struct Shape { int nyt, npt, ct, minb, sb; };
 static const Shape kShapes3D[] = {
   {7, 3, 8, 7, 4}, {7, 3, 8, 7, 1}, {7, 3, 16, 5, 4}, {7, 4, 16, 3, 4}, {7, 2, 16, 6, 4}, {3, 6, 16, 3, 0}, {7, 6, 16, 2, 4}, {7, 3, 16, 4, 0},
