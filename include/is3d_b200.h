@@ -9,6 +9,8 @@
  * momentum tables and the delta-f coefficient tables -- as plain pointers and sizes, and add the result into a
  * caller-owned spectra array with the reference's layout.  INTEGRATION.md shows the few lines that replace the three
  * call sites.  No C++/torch types cross this boundary; all functions return 0 or an IS3D_ERR_* code, never exit().
+ * Further down: operation = 0 (calculate_dN_dX{,_feqmod}, smooth_kernels.cpp:1000-2135), the sampler's mean-yield pass
+ * (calculate_total_yield, emissionfunction_sampling_kernels.cpp:653-831) and the file-level host layer.
  *
  * Threading: one calling host thread per process/GPU.  Multi-GPU runs use one process per GPU, each calling with its
  * own contiguous shard of cells; the caller sums the spectra arrays (one all-reduce).

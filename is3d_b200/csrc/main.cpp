@@ -1,4 +1,4 @@
-// main.cpp -- is3d_b200_run: the RuniS3D.cpp equivalent (reference src/cpp/RuniS3D.cpp:3-12) for operation = 1.
+// main.cpp -- is3d_b200_run: the RuniS3D.cpp equivalent (reference src/cpp/RuniS3D.cpp:3-12) for operation = 1 (spectra) and operation = 0 (spacetime distributions).
 // Run it from a directory laid out like an iS3D checkout (iS3D_parameters.dat, input/, PDG/, tables/,
 // deltaf_coefficients/, results/); it writes the same results/ files as the reference.
 #include "../../include/is3d_b200.h"
@@ -10,7 +10,7 @@ int main(int argc, char **argv)
   const char *dir = (argc > 1) ? argv[1] : ".";
   is3d_stats st;
   std::memset(&st, 0, sizeof(st));
-  std::printf("is3d_b200: smooth Cooper-Frye spectra on the GPU (drop-in for iS3D operation = 1)\n");
+  std::printf("is3d_b200: smooth Cooper-Frye spectra on the GPU (drop-in for iS3D operation = 1 and 0)\n");
   const int rc = is3d_b200_run_workdir(dir, nullptr, 0, nullptr, 0, &st);
   if (rc != IS3D_OK) {
     std::fprintf(stderr, "is3d_b200: failed: %s\n", is3d_b200_strerror(rc));
