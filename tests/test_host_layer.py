@@ -119,6 +119,28 @@ def test_missing_parameter_is_an_error(fx):
         assert lib.is3d_b200_host_dump(wd.encode(), os.path.join(wd, "x.bin").encode()) == 6
 
 
+def test_operation_dispatch_rules(fx):
+    """what the host layer accepts: operation 1 (spectra) and 0 (spacetime distributions, viscous hydro only); the sampler,
+    resonance decays (disabled inside the reference itself) and mode 2 + operation 0 are refused with IS3D_ERR_UNSUPPORTED"""
+    lib = api.lib()
+    lib.is3d_b200_host_error.restype = C.c_char_p
+
+    def rc_for(**params):
+        with tempfile.TemporaryDirectory() as wd:
+            workdir.materialize(wd, fixture=fx, **params)
+            rc = lib.is3d_b200_host_dump(wd.encode(), os.path.join(wd, "x.bin").encode())
+            return rc, lib.is3d_b200_host_error().decode()
+
+    assert rc_for(operation=1)[0] == 0
+    assert rc_for(operation=0)[0] == 0
+    rc, msg = rc_for(operation=2)
+    assert rc == 2 and "sampler" in msg
+    rc, msg = rc_for(operation=1, do_resonance_decays=1)
+    assert rc == 2 and "resonance" in msg
+    rc, msg = rc_for(operation=0, mode=2)
+    assert rc == 2 and "anisotropic" in msg
+
+
 def test_df_tables_and_grids(fx):
     with tempfile.TemporaryDirectory() as wd:
         workdir.materialize(wd, fixture=fx, hrg_eos=2)
