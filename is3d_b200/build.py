@@ -20,6 +20,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 # (source, extra flags).  cf_prepare.cu keeps separate multiply/add so the per-cell set-up rounds like the reference.
 SOURCES = [
     ("cf_kernels.cu", []),
+    ("cf_factored.cu", []),
     ("cf_prepare.cu", ["-fmad=false"]),
     ("cf_api.cu", []),
     ("host_math.cpp", []),

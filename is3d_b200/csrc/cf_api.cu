@@ -245,13 +245,20 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   if (iq && iq->mode == 2 && !dim2) return fail(IS3D_ERR_ARGUMENT, "per-slot integration is a 2+1D pass");
   if (iq && (!iq->pT_weight || !iq->phi_weight)) return fail(IS3D_ERR_ARGUMENT, "pT / phi quadrature weights missing");
   // tile_variant: 0 = model default (tuned on B200, see profiles/), k > 0 = table entry k - 1 (tuning / tests)
-  int variant;
-  if (opt.tile_variant >= 1 && opt.tile_variant <= 16) variant = opt.tile_variant - 1;
+  // 17..20 = shapes of the factored kernel (cf_factored.cu; linear-df models on 3+1D tiles), the default where it applies
+  int variant, fvariant = -1;
+  const bool f_ok = factored_supported(model, L);
+  if (opt.tile_variant >= 1 && opt.tile_variant <= kNumVariants) variant = opt.tile_variant - 1;
+  else if (opt.tile_variant > kNumVariants && opt.tile_variant <= kNumVariants + kNumFactoredVariants) {
+    if (!f_ok) return fail(IS3D_ERR_ARGUMENT, "tile_variant 17..20 (factored kernel) needs df_mode 1/2 on 3+1D tiles");
+    variant = opt.tile_variant - 1; fvariant = variant - kNumVariants;
+  }
+  else if (f_ok) { fvariant = 0; variant = kNumVariants + fvariant; }
   else if (sum_slots) variant = (model == M_FEQMOD || model == M_VAH) ? 12 : (model == M_IDEAL ? 13 : 10);
   else variant = (model == M_VAH || model == M_FEQMOD) ? 11 : 9;
-  (void)dim2_early;
   int nyt, npt, ct, max_warps;
-  hot_variant_shape(variant, sum_slots ? 1 : 0, &nyt, &npt, &ct, &max_warps);
+  if (fvariant >= 0) factored_variant_shape(fvariant, &nyt, &npt, &ct, &max_warps);
+  else hot_variant_shape(variant, sum_slots ? 1 : 0, &nyt, &npt, &ct, &max_warps);
   L.nst = sum_slots ? L.n_slots : nyt;
   L.n_ytiles = sum_slots ? 1 : (L.n_slots + nyt - 1) / nyt;
   L.npt = npt; L.n_ptiles = (L.n_phi + npt - 1) / npt;
@@ -489,15 +496,19 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   hp.n_chunks = n_chunks; hp.n_groupblocks = n_groupblocks; hp.n_warps = n_warps;
   hp.regulate_thr = fl->regulate_deltaf ? 0x3ff00000 : 0x7ff80000;
   hp.one_hi = 0x3ff00000;
+  hp.reg_lo = fl->regulate_deltaf ? 0 : (int)0x80000000; hp.reg_hi = fl->regulate_deltaf ? 0x40000000 : 0x7fffffff;
+  hp.reg_chk = fl->regulate_deltaf ? 0x3fffffffu : 0xffffffffu;
   hp.outflow_thr = (fl->outflow && !vah) ? 0LL : (long long)0x8000000000000000ULL;   // the anisotropic kernel has no Theta(p.dsigma)
   const double hbarC = 0.197327053;
+  hp.pT_max = *std::max_element(gr->pT, gr->pT + gr->n_pT);
   hp.prefactor = vah ? 1.0 / (8.0 * (M_PI * M_PI * M_PI)) / hbarC / hbarC / hbarC      // smooth_kernels.cpp:2146
                      : pow(2.0 * M_PI * hbarC, -3);                                      // :36, :400
   if (iq) {
     hp.integ_mode = iq->mode; hp.integ_sl = integ_sl; hp.chunk_tiles = chunk_tiles_d;
     hp.pT_weight = wpT_d; hp.phi_weight = wphi_d; hp.integ = g_ws.integ.as<double>();
   }
-  CU_CHECK(launch_hot(model, hp, variant, st, nullptr));
+  if (fvariant >= 0) CU_CHECK(launch_factored(model, hp, fvariant, st, nullptr));
+  else CU_CHECK(launch_hot(model, hp, variant, st, nullptr));
   stt.gpu_launches++;
   int reduce_sets = 1;
   PrepCounters cnt; memset(&cnt, 0, sizeof(cnt));
@@ -510,7 +521,11 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
       hl.Y = g_ws.Y2.as<double>(); hl.P = g_ws.P2.as<double>(); hl.S = g_ws.S2.as<double>();
       hl.partial = hp.partial + (size_t)n_chunks * n_bins; hl.renorm = nullptr;
       if (iq) hl.integ = hp.integ + integ_bytes / 8;
-      CU_CHECK(launch_hot(fl->df_mode == 3 ? M_LINCE : M_JONAHLIN, hl, variant, st, nullptr));
+      // the linear branch runs on the factored kernel when one of its shapes has this register tile
+      const int lin_model = fl->df_mode == 3 ? M_LINCE : M_JONAHLIN;
+      const int lin_f = factored_supported(lin_model, L) ? factored_match(nyt, npt) : -1;
+      if (lin_f >= 0) CU_CHECK(launch_factored(lin_model, hl, lin_f, st, nullptr));
+      else CU_CHECK(launch_hot(lin_model, hl, variant, st, nullptr));
       stt.gpu_launches++;
       reduce_sets = 2;
     }

@@ -73,7 +73,10 @@ struct HotParams {
   int n_chunks, n_groupblocks, n_warps;
   long long outflow_thr;                           // bit pattern threshold of the p.dsigma > 0 test
   double prefactor;
+  double pT_max;                                   // largest entry of the pT table (factored kernel: range check of pT B)
   int regulate_thr;                                // high-word threshold of |df| >= 1, see clamp_unit()
+  int reg_lo, reg_hi;                              // factored kernel: bounds of the high word of g = 1 + df (0, 0x40000000 | INT_MIN, INT_MAX)
+  unsigned reg_chk;                                // ... and the unsigned high word above which a member needs the clamp
   int one_hi;                                      // 0x3ff00000 (high word of 1.0) as a run-time value, see clamp_unit()
   // operation = 0 (spacetime distributions): momentum-integrated epilogue instead of the spectra bins
   int integ_mode;                                  // 0 spectra; 1 sum over (slot, phi, pT) per chunk; 2 per slot, sum over (phi, pT)
@@ -101,5 +104,14 @@ cudaError_t launch_yield(const RawCells &cells, const PrepTables &tab, int df_mo
                          PrepCounters *counters, cudaStream_t st);
 cudaError_t launch_fp64_peak(double *sink, int iters, cudaStream_t st, int *blocks, int *threads, long long *dfma_per_thread);
 void hot_variant_shape(int variant, int dim2, int *nyt, int *npt, int *ct, int *max_warps);
+// factored kernel (cf_factored.cu): linear-df models, 3+1D tiles only
+constexpr int kNumVariants = 16;             // register-tile variants of cf_kernel (is3d_options.tile_variant 1..16)
+constexpr int kNumFactoredVariants = 4;      // shapes of cf_factored_kernel (tile_variant 17..20)
+bool factored_supported(int model, const Layout &L);
+void factored_variant_shape(int fvariant, int *nyt, int *npt, int *ct, int *max_warps);
+int factored_match(int nyt, int npt);        // factored shape with this register tile, or -1
+cudaError_t launch_factored(int model, const HotParams &hp, int fvariant, cudaStream_t st, size_t *smem_out);
+// slot records of padding / skipped cells carry this A = u.p / (mT T): every evaluation is dead (exp overflows, f = 0 exactly)
+constexpr double kDeadSlotA = 1.0e6;
 
 }  // namespace is3d

@@ -16,7 +16,9 @@
 // against the 85 flops of the reference's inner loop -- cosh/sinh, the divisions and the tensor contraction
 // are hoisted into the per-cell records by cf_prepare.cu, the lane-independent shear cross term into a per-tile pair table.
 #include "cf_internal.h"
+#include <algorithm>
 #include "cf_device.cuh"
+#include "cf_epilogue.cuh"
 
 namespace is3d {
 
@@ -475,63 +477,9 @@ cf_kernel(const HotParams hp)
     if (threadIdx.x == 0 && t + kStages < n_my_tiles) issue(t + kStages);
   }
 
-  // ---- operation = 0 epilogue: integrate over (pT, phi) with the table weights (smooth_kernels.cpp:1284-1371), one
-  //      number per (species, chunk) -- or per (species, slot) -- instead of the spectra bins
-  if (hp.integ_mode) {
-    constexpr int NJ = DIM2 ? 1 : NYT;
-    const int per_slot = (hp.integ_mode == 2) ? NJ : 1;
-    double *red = stage_base;                           // [per_slot][blockDim.x]; every stage has been consumed
-    const double wl = lane_valid ? hp.pT_weight[ipT] * (hp.prefactor * hp.degeneracy[ipart]) : 0.0;
-    double tot = 0.0;
-#pragma unroll
-    for (int j = 0; j < NJ; j++) {
-      double sj = 0.0;
-      const bool slot_ok = DIM2 || ty * NYT + j < L.n_slots;
-#pragma unroll
-      for (int k = 0; k < NPT; k++) {
-        const int iphi = tp * NPT + k;
-        if (slot_ok && iphi < L.n_phi) sj = fma(hp.phi_weight[iphi], acc[(DIM2 ? 0 : j * NPT) + k], sj);
-      }
-      if (hp.integ_mode == 2) red[j * blockDim.x + threadIdx.x] = wl * sj;
-      tot += sj;
-    }
-    if (hp.integ_mode == 1) red[threadIdx.x] = wl * tot;
-    __syncthreads();
-    const int pair0 = gb * (int)blockDim.x, n_pairs = L.n_species * L.n_pT;
-    const int s_first = pair0 / L.n_pT;
-    for (int w = threadIdx.x; w < per_slot * hp.integ_sl; w += blockDim.x) {
-      const int j = w / hp.integ_sl, sl = w - j * hp.integ_sl;
-      const int sidx = s_first + sl;
-      int lo = sidx * L.n_pT, hi = lo + L.n_pT;
-      if (lo < pair0) lo = pair0;
-      if (hi > pair0 + (int)blockDim.x) hi = pair0 + (int)blockDim.x;
-      if (hi > n_pairs) hi = n_pairs;
-      double v = 0.0;
-      for (int q = lo; q < hi; q++) v += red[j * blockDim.x + (q - pair0)];
-      const int64_t unit = (hp.integ_mode == 2) ? (int64_t)chunk * (L.n_ytiles * NJ) + ty * NJ + j : (int64_t)chunk * L.n_ytiles + ty;
-      hp.integ[((unit * L.n_ptiles + tp) * hp.n_groupblocks + gb) * hp.integ_sl + sl] = v;
-    }
-    return;
-  }
-
-  // ---- epilogue: partial[chunk][ipart + n_species (ipT + n_pT (iphi + n_phi iy))]
-  if (lane_valid) {
-    const double scale = hp.prefactor * hp.degeneracy[ipart];
-    const int64_t n_bins = (int64_t)L.n_species * L.n_pT * L.n_phi * L.n_y_out;
-    double *out = hp.partial + (int64_t)chunk * n_bins;
-#pragma unroll
-    for (int j = 0; j < (DIM2 ? 1 : NYT); j++) {
-      const int iy = DIM2 ? 0 : ty * NYT + j;
-      if (iy >= (DIM2 ? 1 : L.n_slots)) continue;
-#pragma unroll
-      for (int k = 0; k < NPT; k++) {
-        const int iphi = tp * NPT + k;
-        if (iphi >= L.n_phi) continue;
-        const int64_t iS3D = (int64_t)ipart + (int64_t)L.n_species * ((int64_t)ipT + (int64_t)L.n_pT * ((int64_t)iphi + (int64_t)L.n_phi * iy));
-        out[iS3D] = scale * acc[(DIM2 ? 0 : j * NPT) + k];
-      }
-    }
-  }
+  // ---- epilogue (cf_epilogue.cuh): spectra bins of this chunk, or the momentum-integrated numbers of operation = 0;
+  //      every stage has been consumed, so the stage area doubles as the block scratch (launch_one sizes it for that)
+  hot_epilogue<NYT, NPT, DIM2>(hp, acc, stage_base, chunk, gb, ty, tp, lane_valid, ipart, ipT);
 }
 
 // ------------------------------------------------------------------------------------------------ reduce
@@ -597,7 +545,6 @@ static const Shape kShapes3D[] = {
 static const Shape kShapes2D[] = {
   {1, 3, 1, 4, 0}, {1, 4, 1, 4, 0}, {1, 6, 1, 3, 0}, {1, 8, 1, 3, 0}, {1, 2, 1, 5, 0}, {1, 12, 1, 2, 0}, {1, 4, 1, 3, 0}, {1, 1, 1, 6, 0},
   {1, 6, 1, 3, 3}, {1, 3, 1, 4, 1}, {1, 4, 1, 4, 3}, {1, 4, 1, 3, 1}, {1, 6, 1, 3, 1}, {1, 8, 1, 3, 3}, {1, 3, 1, 5, 1}, {1, 12, 1, 2, 3}};
-constexpr int kNumVariants = 16;
 
 void hot_variant_shape(int variant, int dim2, int *nyt, int *npt, int *ct, int *max_warps)
 {
@@ -614,7 +561,9 @@ static cudaError_t launch_one(const HotParams &hp, cudaStream_t st, size_t *smem
   const int nst = DIM2 ? L.nst : NYT;
   const size_t stage_doubles = (size_t)L.ct * nst * RY + (size_t)L.ct * NPT * kRec + (size_t)L.ct * kScal;
   constexpr bool PAIR = !DIM2 && (MODEL == M_LIN14 || MODEL == M_LINCE || MODEL == M_JONAHLIN || MODEL == M_VAH || MODEL == M_FEQMOD);
-  const size_t smem = kStages * stage_doubles * 8 + kStages * sizeof(uint64_t) + (PAIR ? (size_t)L.ct * NYT * NPT * 8 : 0);
+  // operation = 0: the epilogue reuses the stage area as [per_slot][threads] scratch -- make sure it is large enough
+  const size_t stage_bytes = std::max(kStages * stage_doubles * 8, (hot_epilogue_scratch_bytes(hp, NYT, DIM2, hp.n_warps * 32) + 15) & ~(size_t)15);
+  const size_t smem = stage_bytes + kStages * sizeof(uint64_t) + (PAIR ? (size_t)L.ct * NYT * NPT * 8 : 0);
   if (smem_out) *smem_out = smem;
   auto kern = cf_kernel<MODEL, NYT, NPT, DIM2, MINB, SB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

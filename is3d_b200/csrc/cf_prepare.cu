@@ -48,7 +48,8 @@ __device__ __forceinline__ int64_t source_cell(const RawCells &cells, const Layo
 constexpr int kPrepCells = 16;      // cells per prepare block
 constexpr int kPrepThreads = 128;
 
-__device__ __forceinline__ void dummy_slot(double *r) { r[0] = 8.0; r[1] = 0.0; r[2] = 0.0; r[3] = 0.0; r[4] = 0.0; r[5] = 0.0; }
+// padding, skipped (u.dsigma <= 0) and out-of-table cells: A = kDeadSlotA makes every evaluation dead, the hot kernels skip the group
+__device__ __forceinline__ void dummy_slot(double *r) { r[0] = kDeadSlotA; r[1] = 0.0; r[2] = 0.0; r[3] = 0.0; r[4] = 0.0; r[5] = 0.0; }
 __device__ __forceinline__ void dummy_phi(double *r) { r[0] = 0.0; r[1] = 0.0; r[2] = 0.0; r[3] = 0.0; r[4] = 0.0; r[5] = 0.0; }
 
 // DFM = 1 (14 moment) or 2 (Chapman-Enskog)
@@ -270,7 +271,7 @@ prepare_feqmod_kernel(RawCells cells, PrepTables tab, Layout L, int include_shea
   if (threadIdx.x < kPrepCells) {
     const int64_t i = source_cell(cells, L, cell0 + threadIdx.x);
     CellFM c; c.valid = 0; c.breaks_down = 0; c.detA = 1.0; c.eta_scale = 1.0;
-    double sF[4] = {44.0, 0.0, 0.0, 0.0};        // feqmod scalars: 1/T_mod^2, per-cell renorm (Jonah), -, -
+    double sF[4] = {1.0e12, 0.0, 0.0, 0.0};      // feqmod scalars: 1/T_mod^2 (invalid cell: E'/T_mod = 1e6 m, dead), per-cell renorm (Jonah), -, -
     double sL[4] = {0.0, 0.0, 0.0, 0.0};         // linear scalars: K0, K2, K3, -
     double aux[8] = {0, 0, 0, 0, 0, 0, 0, 0};    // per-cell inputs of the (cell, species) renormalisation kernel
     if (i >= 0) {
@@ -394,7 +395,7 @@ prepare_feqmod_kernel(RawCells cells, PrepTables tab, Layout L, int include_shea
         }
       }
     }
-    if (!c.valid) { sF[0] = 44.0; sF[1] = 0.0; sL[0] = sL[1] = sL[2] = 0.0; aux[5] = 0.0; }
+    if (!c.valid) { sF[0] = 1.0e12; sF[1] = 0.0; sL[0] = sL[1] = sL[2] = 0.0; aux[5] = 0.0; }
     sc_[threadIdx.x] = c;
     const int64_t ip = cell0 + threadIdx.x;
     if (ip < L.n_cells_pad) {
@@ -415,7 +416,8 @@ prepare_feqmod_kernel(RawCells cells, PrepTables tab, Layout L, int include_shea
     double *rf = YF + off, *rl = YL + off;
     const CellFM &c = sc_[lc];
     dummy_slot(rl);
-    rf[0] = 0.0; rf[1] = 0.0; rf[2] = 0.0; rf[3] = 0.0; rf[4] = 0.0; rf[5] = 0.0;
+    // slots the other record set owns (and padding): |p'| / T_mod >= 1e6 mT, every evaluation dead
+    rf[0] = kDeadSlotA; rf[1] = 0.0; rf[2] = 0.0; rf[3] = kDeadSlotA * kDeadSlotA; rf[4] = 0.0; rf[5] = 0.0;
     if (!c.valid || j >= L.n_slots) continue;
     double yv, eta, wgt;
     if (L.dim2) { yv = 0.0; eta = tab.slot_y[j]; wgt = tab.slot_w[j]; }
@@ -588,7 +590,7 @@ prepare_vah_kernel(RawCells cells, PrepTables tab, Layout L, int include_shear, 
     const int ty = j / L.nst, jj = j - ty * L.nst;
     double *r = Y + (((int64_t)ty * L.n_cells_pad + i) * L.nst + jj) * kRecVah;
     const CellVAH &c = sc_[lc];
-    if (!c.valid || j >= L.n_slots) { r[0] = 8.0; for (int q = 1; q < kRecVah; q++) r[q] = 0.0; continue; }
+    if (!c.valid || j >= L.n_slots) { r[0] = kDeadSlotA; for (int q = 1; q < kRecVah; q++) r[q] = 0.0; continue; }
     double yv, eta, wgt;
     if (L.dim2) { yv = 0.0; eta = tab.slot_y[j]; wgt = tab.slot_w[j] * tab.eta_delta; }        // :2175-2183
     else        { yv = tab.slot_y[j]; eta = c.eta; wgt = 1.0; }

@@ -308,11 +308,102 @@ def test_full_size_cfg3_properties(fx):
     shuffled, _ = api.smooth_spectra(fl, {k: v[perm].contiguous() for k, v in dev.items()}, sp, g, tab, None, memory="device")
     w = whole.cpu().numpy()
     assert np.all(w >= 0.0) and np.isfinite(w).all() and (w > 0).mean() > 0.99
+    _check_sampled_bins_full_size(fl, cells, sp, g, tab, None, w)
     for other in (parts, shuffled):
         o = other.cpu().numpy()
         assert np.array_equal(o == 0.0, w == 0.0)
         nz = w != 0.0
         assert np.max(np.abs(o[nz] - w[nz]) / w[nz]) < 1e-12
+
+
+
+# bins of the 1 M-cell check: light and heavy species, soft to hard pT, three azimuths, backward / central / forward rapidity
+SAMPLE_SPECIES = (0, 3, 17, 60, 150, 304)
+SAMPLE_PT = (1, 9, 16, 22)
+SAMPLE_PHI = (0, 7, 19)
+SAMPLE_Y = (0, 4, 10, 13, 20)
+
+
+def _check_sampled_bins_full_size(fl, cells, sp, g, tab, gla, dN_gpu, vah=False):
+    """The oracle over ALL cells of the surface for a product sub-grid of bins (every bin's arithmetic is independent of the
+    other bins, so the sub-grid values equal the full run's): 6 x 4 x 3 x 5 = 360 bins x 1 M cells = 3.6e8 oracle evaluations."""
+    from oracle import cf_oracle as cfo
+    sps = {k: np.ascontiguousarray(np.asarray(v)[list(SAMPLE_SPECIES)]) for k, v in sp.items()}
+    gs = dict(g)
+    gs["pT"] = g["pT"][list(SAMPLE_PT)]; gs["pT_weight"] = g["pT_weight"][list(SAMPLE_PT)]
+    gs["phi"] = g["phi"][list(SAMPLE_PHI)]; gs["phi_weight"] = g["phi_weight"][list(SAMPLE_PHI)]
+    gs["y"] = g["y"][list(SAMPLE_Y)]; gs["y_weight"] = g["y_weight"][list(SAMPLE_Y)]
+    ref, _, _ = cfo.smooth(fl, cells, sps, gs, tab, gla, vah=vah)
+    ref = ref.reshape(len(SAMPLE_Y), len(SAMPLE_PHI), len(SAMPLE_PT), len(SAMPLE_SPECIES))
+    full = dN_gpu.reshape(len(g["y"]), len(g["phi"]), len(g["pT"]), len(sp["mass"]))
+    got = full[np.ix_(SAMPLE_Y, SAMPLE_PHI, SAMPLE_PT, SAMPLE_SPECIES)]
+    rep = compare(got.ravel(), ref.ravel())
+    assert rep["ok"], rep
+    assert (ref != 0).mean() > 0.9
+    return rep
+
+
+@pytest.mark.parametrize("workload", ["cfg4ce", "cfg4mike", "cfg4jonah", "cfg5"])
+def test_full_size_other_configs_sampled_bins(fx, workload):
+    """BASELINE configs[3] (Chapman-Enskog, feqmod Mike / Jonah) and configs[4] (anisotropic PL matching) at their stated size,
+    1 M cells x 305 species: 360 sampled bins against the oracle run over the whole surface, 1e-10 per bin."""
+    import torch
+    from common import vah_cells
+    n = 1_000_000
+    sp = tables.species(fx, 1, "chosen_urqmd"); g = tables.grid(fx); tab = tables.df_tables(fx, 1); gla = tables.laguerre(fx)
+    vah = workload == "cfg5"
+    if vah:
+        cells = vah_cells(synthetic.surface_vah(n, synthetic.SEEDS["cfg5"]), fx)
+        fl = tables.flags(df_mode=1, dimension=3); fl["mode"] = 2
+        keys = [k for k in api.SURFACE_FIELDS if k in cells and k not in ("x", "y", "muB", "nB", "Vx", "Vy", "Vn", "T", "P", "E")]
+    else:
+        cells = synthetic.columns_to_cells(synthetic.surface_vh(n, synthetic.SEEDS["cfg3"]), 1)
+        dfm = {"cfg4ce": 2, "cfg4mike": 3, "cfg4jonah": 4}[workload]
+        fl = tables.flags(df_mode=dfm, dimension=3)
+        if dfm == 4:
+            tab.update(jonah_tables(cells, fx, 1, gla))
+        keys = ["tau", "eta", "dat", "dax", "day", "dan", "ux", "uy", "un", "T", "P", "E", "pixx", "pixy", "pixn", "piyy", "piyn", "bulkPi"]
+    dev = {k: torch.from_numpy(np.ascontiguousarray(cells[k])).cuda() for k in keys}
+    dN, st = api.smooth_spectra(fl, dev, sp, g, tab if not vah else None, gla if not vah else None, memory="device")
+    assert st["evaluations"] == n * 305 * 16128 and st["cells_skipped_udsigma"] == 0
+    rep = _check_sampled_bins_full_size(fl, cells, sp, g, tab if not vah else None, gla if not vah else None, dN.cpu().numpy(), vah=vah)
+    print(workload, rep, st["kernel_ms"])
+
+
+@pytest.mark.parametrize("case", ["df2", "df3", "df4", "vah"])
+def test_all_bins_against_oracle_at_full_species(fx, case):
+    """every one of the 4.9 M bins of the 305-species list against the oracle on a 48-cell prefix of the BASELINE surface,
+    for the models test_sampled_bins_against_oracle_at_full_species (df_mode 1) does not cover"""
+    from oracle import cf_oracle as cfo
+    from common import vah_cells
+    n = 48
+    sp = tables.species(fx, 1, "chosen_urqmd"); g = tables.grid(fx); tab = tables.df_tables(fx, 1); gla = tables.laguerre(fx)
+    if case == "vah":
+        cells = vah_cells(synthetic.surface_vah(n, synthetic.SEEDS["cfg5"]), fx)
+        fl = tables.flags(df_mode=1, dimension=3); fl["mode"] = 2
+        ref, _, _ = cfo.smooth(fl, cells, sp, g, vah=True)
+        dN, _ = api.smooth_spectra(fl, cells, sp, g, None, None)
+        cond = None
+    else:
+        cells = synthetic.columns_to_cells(synthetic.surface_vh(n, synthetic.SEEDS["cfg3"]), 1)
+        dfm = int(case[2])
+        fl = tables.flags(df_mode=dfm, dimension=3)
+        if dfm == 4:
+            tab.update(jonah_tables(cells, fx, 1, gla))
+        cond = np.zeros(305 * 32 * 24 * 21) if dfm == 2 else None
+        ref, _, bd = cfo.smooth(fl, cells, sp, g, tab, gla, conditioning=cond)
+        dN, st = api.smooth_spectra(fl, cells, sp, g, tab, gla)
+        assert st["cells_feqmod_breakdown"] == bd
+    plain = compare(dN, ref)
+    nz = ref != 0
+    rel = np.abs(dN[nz] - ref[nz]) / np.abs(ref[nz])
+    print(case, plain, int((rel > REL_TOL).sum()))
+    if cond is None:
+        assert plain["ok"], plain
+    else:
+        # Chapman-Enskog df: a bin dominated by one cell whose 1 + df nearly cancels carries the reference's own rounding noise
+        assert (rel > REL_TOL).sum() <= 20 and plain["max_rel"] < 1e-8 and plain["zeros_match"], plain
+        assert compare(dN, ref, conditioning=cond)["ok"]
 
 
 # ---------------------------------------------------------------------------------------- every compiled tile variant
@@ -325,8 +416,13 @@ def test_every_tile_variant(name, fx):
         fl, cells, sp, g, _ = vah_problem(gold["recipe"], fx); tab = gla = None
     else:
         fl, cells, sp, g, tab, gla = problem_from_recipe(gold["recipe"], fx)
-    for variant in range(1, 17):
+    factored = name in ("s3_df1", "s3_df2")            # linear-df model as the main pass on 3+1D tiles: cf_factored.cu shapes 17..20
+    for variant in range(1, 21 if factored else 17):
         dN, st = api.smooth_spectra(fl, cells, sp, g, tab, gla, tile_variant=variant)
         assert st["tile_variant"] == variant - 1
         rep = compare(dN, gold["dN"])
         assert rep["ok"], (name, variant, rep)
+    if not factored:
+        with pytest.raises(api.Is3dError) as e:
+            api.smooth_spectra(fl, cells, sp, g, tab, gla, tile_variant=17)
+        assert e.value.code == 1
