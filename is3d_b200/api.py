@@ -153,17 +153,28 @@ def vah_cells(columns, fx):
     f = lib().is3d_b200_vah_anisotropy
     f.argtypes = [C.c_int64, _D, _D, _D, _D, _D]
     _check(f(n, m.host(a[:, 13]), m.host(a[:, 14]), m.host(a[:, 15]), aL.ctypes.data_as(_D), Lam.ctypes.data_as(_D)))
+    out = vah_coefficients(fx, Lam, aL)
+    cells["aL"] = aL; cells["Lambda"] = Lam
+    for k in range(5):
+        cells["c%d" % k] = out[k]
+    return cells
+
+
+def vah_coefficients(fx, Lambda_GeV, aL):
+    """Per-cell c0..c4 [GeV units] of the anisotropic model from the (Lambda [fm^-1], alpha_L) tables: is3d_b200_vah_coefficients
+    (C++ host layer).  Raises Is3dError(IS3D_ERR_TABLE_RANGE) if a cell lies outside the table (the reference leaves garbage)."""
+    m = _Marshal(False)
+    n = len(aL)
     nL, naL = int(fx["df_vah/nL"]), int(fx["df_vah/naL"])
     Lg = fx["df_vah/L_col"][:nL]; ag = fx["df_vah/aL_col"][::nL]
     tabs = [np.ascontiguousarray(fx["df_vah/c%d" % k].reshape(naL, nL).T) for k in range(5)]      # -> [iL][iaL]
     out = [np.zeros(n) for _ in range(5)]
     g = lib().is3d_b200_vah_coefficients
     g.argtypes = [C.c_int32, C.c_int32, _D, _D, _D, _D, _D, _D, _D, C.c_int64, _D, _D, _D, _D, _D, _D, _D]
-    _check(g(nL, naL, m.host(Lg), m.host(ag), *[m.host(t) for t in tabs], n, m.host(Lam), m.host(aL), *[o.ctypes.data_as(_D) for o in out]))
-    cells["aL"] = aL; cells["Lambda"] = Lam
-    for k in range(5):
-        cells["c%d" % k] = out[k]
-    return cells
+    rc = g(nL, naL, m.host(Lg), m.host(ag), *[m.host(t) for t in tabs], n, m.host(Lambda_GeV), m.host(aL), *[o.ctypes.data_as(_D) for o in out])
+    if rc:
+        raise Is3dError(rc, lib().is3d_b200_host_error().decode() or lib().is3d_b200_strerror(rc).decode())
+    return out
 
 
 def _is_torch(x):

@@ -1,28 +1,32 @@
 // cf_factored.cu -- second-generation hot kernel for the linear-delta-f models in 3+1D (sm_100a): the loop nest of
 // EmissionFunctionArray::calculate_dN_pTdpTdphidy (reference src/cpp/emissionfunction_smooth_kernels.cpp:246-347) for
-// df_mode 1 (14 moment), 2 (Chapman-Enskog), Jonah's linearised df and the ideal f_eq.
+// df_mode 1 (14 moment), 2 (Chapman-Enskog), Jonah's linearised df and the ideal f_eq, for species lists of >= 16 hadrons.
 //
-// Same work decomposition and TMA cell stream as cf_kernels.cu (lane = (species, pT), thread = NYT x NPT register tile, block =
-// bin tile x cell chunk).  What is new is the arithmetic per evaluation:
+// Work decomposition
+//   lane   <-> one SPECIES; the 32 lanes of a warp are 32 consecutive species of the chosen list (consecutive entries of a PDG
+//              list have similar masses) and every warp of a block works on the SAME pT point.  u.p/T = mT A[slot] - pT B[phi] is
+//              then nearly the same for all lanes of a warp: dead / dilute / ultra-dilute groups are decided per WARP with
+//              votes, and the one branch taken is the one all lanes need.  (cf_kernels.cu puts the 32 pT points of one species in
+//              a warp: pT spans 0.001-40 GeV there, so a warp straddles every class.)
+//   thread     register tile of NYT rapidity slots x NPT phi points, walks the cells of its chunk.
+//   block      up to 4 warps (128 species) x one pT point x one (y-tile, phi-tile) x one contiguous cell chunk; cell tiles are
+//              streamed global -> shared with cp.async.bulk (TMA) through a kStages-deep mbarrier pipeline.
+//   grid       species blocks x pT points x bin tiles x cell chunks; partial[chunk][bin] + reduce_kernel as in cf_kernels.cu.
 //
-//  1. Factored exponential.  u.p/T = x = mT A[slot] - pT B[phi], so e^{-x} = e^{-mT A[slot]} e^{+pT B[phi]}: one exponential per
-//     (cell, slot) and one per (cell, phi) instead of one per evaluation, each kept as mantissa x 2^n (exp_neg_poly).  An
-//     evaluation multiplies two mantissas (1 DMUL) and adds two integers; the exponent n = n_slot + n_phi also classifies the
-//     group (dead / sub-normal / dilute / ultra-dilute) with integer min/max, so x itself is never formed on the fast path.
-//  2. Merged bilinear delta-f (14 moment).  df / feqbar = mT^2 Qyy + pT^2 Qpp + K0 m^2 + mT pT pair + K2 x^2, and
-//     K2 x^2 = mT^2 K2 A^2 + pT^2 K2 B^2 - 2 mT pT K2 A B has the same three shapes: it is folded into Qyy, Qpp and the pair
-//     table by the block once per (cell, slot / phi / pair) -- 2 FP64 instructions per evaluation instead of 4.
-//  3. g = 1 + df is formed directly (the reference multiplies f_eq (1 + df), :330) and regulate_deltaf clamps g to [0, 2] on its
-//     high word; one unsigned max3 per group decides whether any member needs the clamp.
-//  4. Occupation factor 1 / (1 + Theta a), a = e^{-x}: exactly 1 for a < 2^-54 ("ultra dilute", 6 FP64 instructions per
-//     evaluation), 1 - Theta a + a^2 for a < 2^-18 (10), MUFU seed + Newton otherwise (12).
-//  5. Derived per-tile tables.  Right after a cell tile lands, the block turns the streamed records into the tables the inner
-//     loop reads (slot: A, Cp, Qyy'; phi: B, D, Qpp'; pair'; cell: K0, K2, K3, max B) -- double buffered, so a tile costs ONE
-//     __syncthreads and its TMA stage is released before the inner loop starts.
-//
-// Dead groups (every member's exp(x) overflows in the reference, f = 0 exactly) are skipped before their exponential is
-// evaluated: mT A > ln(DBL_MAX) + pT max_k B[k] is a high-word compare.  Groups with a member near the overflow / sub-normal
-// boundary take the exact per-member path of cf_device.cuh (exp_neg_slow), so the zero pattern is the reference's.
+// Arithmetic per evaluation
+//   1. Factored exponential: e^{-x} = e^{-mT A[slot]} e^{+pT B[phi]}.  The phi factor does not depend on the species any more: the
+//      block computes it ONCE per (cell, phi) into shared memory while it turns the streamed records into the tables of the inner
+//      loop (pT B, pT D, pT^2 Qpp, pT (R2 U2 - R1 U1), ...); a thread evaluates one exponential per (cell, slot) and multiplies
+//      mantissas (1 DMUL) / adds binary exponents per evaluation.  The exponent sum also classifies the group, so nothing of this
+//      needs x itself.
+//   2. g = 1 + df is formed directly (the reference multiplies f_eq (1 + df), :330); regulate_deltaf clamps g to [0, 2] on its
+//      high word.
+//   3. Occupation factor 1 / (1 + Theta a), a = e^{-x}: exactly 1 for a < 2^-54 (ultra dilute), 1 - Theta a + a^2 for a < 2^-18,
+//      MUFU seed + Newton otherwise -- chosen per warp.
+//   4. The derived tables are double buffered: a tile costs ONE __syncthreads and its TMA stage is released before the inner loop.
+// Dead slots (every member's exp(x) overflows in the reference, f = 0 exactly) are skipped before their exponential is evaluated:
+// mT A > ln(DBL_MAX) + max_k pT B[k] is a high-word compare.  Members within ~3 units of the overflow / sub-normal boundary are
+// evaluated by late_member() exactly as cf_kernels.cu decides them (x itself, exp_neg), so the zero pattern is the reference's.
 #include "cf_internal.h"
 #include <algorithm>
 #include "cf_device.cuh"
@@ -32,14 +36,18 @@ namespace is3d {
 
 namespace {
 
-// exponent classes of a = mantissa (< 4) x 2^n
-constexpr int kNDead = -1031;      // n <= kNDead for every member: a < 2^-1029, x > 713 > ln(DBL_MAX): all terms exactly 0
-constexpr int kNNormal = -1019;    // n >= kNNormal for every member: normal results, exponent insertion is safe
+// exponent classes of a = mantissa (in [0.997, 3.99)) x 2^n
+constexpr int kNDead = -1027;      // n <= kNDead: a < 2^-1025, x > 710.4 > ln(DBL_MAX): the term is exactly 0 in the reference
+constexpr int kNNormal = -1021;    // n >= kNNormal: a >= 0.997 x 2^-1021, a normal number: exponent insertion is exact
 constexpr int kNDilute = -20;      // n <= kNDilute: a < 2^-18
 constexpr int kNUltra = -56;       // n <= kNUltra: a < 2^-54, 1 + Theta a rounds to 1
+constexpr int kNForcedDead = -200000;
 
-constexpr int kDerC = 6;           // doubles per derived cell record: K0, K2, 1 + K3, max_k B, int2 {general-path flag, dead-cell flag}, -
-constexpr double kQLimit = 2000.0; // |pT B| beyond this: the Cody-Waite reduction of cf_device.cuh leaves its exact range -> general path
+constexpr int kDerS = 4;           // derived slot record: A, Cp, Qyy, -
+constexpr int kDerP = 6;           // derived phi record (block's pT folded in): q = pT B, pd = pT D, G0 = pT^2 Qpp, fq, int fm, -
+constexpr int kDerC = 6;           // derived cell record: K0, K2, 1 + K3, int2 {dead_hi, flags}, -, -
+constexpr double kQLimit = 2000.0; // |pT B| beyond this leaves the exact range of the Cody-Waite reduction: late_member() for the cell
+constexpr unsigned kFull = 0xffffffffu;
 
 template <int NPT> struct PairPitch { static constexpr int v = (NPT + 1) & ~1; };
 
@@ -52,34 +60,34 @@ __device__ __forceinline__ double clamp_g(double g, int reg_lo, int reg_hi)
   return __hiloint2double(hc, hc == hi ? __double2loint(g) : 0);
 }
 
-// acc[k] += (pd[k] + cpm) fe[k] g[k] for the members whose p.dsigma passes the outflow test (smooth_kernels.cpp:285); the test is
-// made once per group on the high words (thr_hi = 0: p.dsigma > 0; INT_MIN: outflow off), so the common all-pass case is N plain DFMAs
-template <int N>
-__device__ __forceinline__ void accumulate_group(double *acc, const double (&pd)[N], double cpm, const double (&fe)[N], const double *g, int thr_hi)
+// delta-f polynomial without feqbar: s = bilinear part (mT^2 Qyy + pT^2 Qpp + K0 m^2 + mT pT pair), x = u.p / T
+template <int MODEL>
+__device__ __forceinline__ double df_poly(double s, double x, double K2)
 {
-  double pv[N];
-#pragma unroll
-  for (int k = 0; k < N; k++) pv[k] = pd[k] + cpm;
-  int lo = __double2hiint(pv[0]);
-#pragma unroll
-  for (int k = 1; k < N; k++) lo = min(lo, __double2hiint(pv[k]));
-  if (lo > thr_hi) {
-#pragma unroll
-    for (int k = 0; k < N; k++) acc[k] = fma(pv[k], g ? fe[k] * g[k] : fe[k], acc[k]);
-  } else {
-#pragma unroll
-    for (int k = 0; k < N; k++) accumulate_pos(acc[k], pv[k], g ? fe[k] * g[k] : fe[k], thr_hi);
-  }
+  if (MODEL == M_LIN14) return fma(K2 * x, x, s);                 // + Pi bulk2 (u.p)^2
+  return fma(s, rcp_fast(x), K2 * x);                              // [..] / (u.p) + (..) (u.p)
+}
+
+// One evaluation decided from x itself, for members near the overflow / sub-normal boundary of e^{-x} (and for cells whose pT B
+// leaves the range of the factored form): returns p.dsigma f, exactly 0 where the reference's exp(x) overflows.  Out of line: rare.
+template <int MODEL>
+__device__ __noinline__ double late_member(double x, double s, double pv, double K2, double K31, double sign, int reg_lo, int reg_hi, int thr_hi)
+{
+  if (!exp_finite(x) || __double2hiint(pv) <= thr_hi) return 0.0;
+  const double av = exp_neg(x);
+  const double fb = rcp_fast(fma(sign, av, 1.0));
+  double g = 1.0;
+  if (MODEL != M_IDEAL) g = clamp_g(fma(fb, df_poly<MODEL>(s, x, K2), K31), reg_lo, reg_hi);
+  return pv * ((av * fb) * g);
 }
 
 }  // namespace
 
-template <int MODEL, int NYT, int NPT, int MINB>
-__global__ void __launch_bounds__(kMaxWarps * 32, MINB)
+template <int MODEL, int NYT, int NPT, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 cf_factored_kernel(const HotParams hp)
 {
-  constexpr bool MERGE = (MODEL == M_LIN14);                    // K2 x^2 folded into the bilinear form
-  constexpr bool NEEDX = (MODEL == M_LINCE || MODEL == M_JONAHLIN);   // df contains 1 / (u.p): x is formed per evaluation
+  constexpr bool POLY = (MODEL != M_IDEAL);
   constexpr int PP = PairPitch<NPT>::v;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const Layout &L = hp.L;
@@ -87,32 +95,31 @@ cf_factored_kernel(const HotParams hp)
   const int nthreads = blockDim.x;
   const int y_doubles = CT * NYT * kRec, p_doubles = CT * NPT * kRec, s_doubles = CT * kScal;
   const int stage_doubles = y_doubles + p_doubles + s_doubles;
-  const int der_doubles = CT * (NYT * 4 + NPT * 4 + kDerC + NYT * PP);
+  const int der_doubles = CT * (NYT * kDerS + NPT * kDerP + kDerC + NYT * PP);
   double *stage_base = reinterpret_cast<double *>(smem_raw);
   double *der_base = stage_base + (size_t)kStages * stage_doubles;
   uint64_t *full = reinterpret_cast<uint64_t *>(der_base + 2 * (size_t)der_doubles);
 
-  // ---- task decode: blockIdx -> (group block, y tile, phi tile, cell chunk)
+  // ---- task decode: blockIdx -> (species block, pT point, y tile, phi tile, cell chunk); pT runs fastest, so the blocks that are
+  //      resident together stream the same cells
   const int n_bintiles = hp.n_groupblocks * L.n_ytiles * L.n_ptiles;
   const int chunk = blockIdx.x / n_bintiles;
   int bt = blockIdx.x - chunk * n_bintiles;
+  const int ipT = bt % L.n_pT; bt /= L.n_pT;
   const int tp = bt % L.n_ptiles; bt /= L.n_ptiles;
   const int ty = bt % L.n_ytiles; bt /= L.n_ytiles;
-  const int gb = bt;
+  const int sb = bt;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // ---- this lane's (species, pT)
-  const int idx = (gb * hp.n_warps + warp) * 32 + lane;
-  const bool lane_valid = idx < L.n_species * L.n_pT;
-  const int ipart = lane_valid ? idx / L.n_pT : 0;
-  const int ipT = lane_valid ? idx - ipart * L.n_pT : 0;
+  // ---- this lane's species; the block's pT
+  const int isp = (sb * hp.n_warps + warp) * 32 + lane;
+  const bool lane_valid = isp < L.n_species;
+  const int ipart = lane_valid ? isp : L.n_species - 1;
   const double mass = hp.mass[ipart], sign = hp.sign[ipart], pT = hp.pT[ipT];
   const double nsign = -sign;
   const double m2 = mass * mass, pT2 = pT * pT;
   const double mT2 = m2 + pT2;
   const double mT = sqrt(mT2);
-  const double mTpT = mT * pT;
-  // regulate_deltaf as integer bounds on the high word of g = 1 + df (set by the host, see clamp_g)
   const int reg_lo = hp.reg_lo, reg_hi = hp.reg_hi;
   const int thr_hi = (int)(hp.outflow_thr >> 32);
 
@@ -154,177 +161,154 @@ cf_factored_kernel(const HotParams hp)
     const double *Ys = stage_base + (size_t)st * stage_doubles;
     const double *Ps = Ys + y_doubles;
     const double *Ss = Ps + p_doubles;
-    double *dS = der_base + (size_t)(t & 1) * der_doubles;        // [CT][NYT][4]: A, Cp, Qyy', -
-    double *dP = dS + CT * NYT * 4;                               // [CT][NPT][4]: B, D, Qpp', -
-    double *dC = dP + CT * NPT * 4;                               // [CT][kDerC]
-    double *dX = dC + CT * kDerC;                                 // [CT][NYT][PP]: pair'
+    double *dS = der_base + (size_t)(t & 1) * der_doubles;        // [CT][NYT][kDerS]
+    double *dP = dS + CT * NYT * kDerS;                           // [CT][NPT][kDerP]
+    double *dC = dP + CT * NPT * kDerP;                           // [CT][kDerC]
+    double *dX = dC + CT * kDerC;                                 // [CT][NYT][PP]: pT (R2 U2 - R1 U1)
 
-    // ---- derive this tile's tables (block-cooperative, ~2 items per thread)
+    // ---- derive this tile's tables (block-cooperative, a few items per thread)
 #pragma unroll 1
     for (int w = threadIdx.x; w < CT * NYT; w += nthreads) {
-      const int c = w / NYT;
       const double *yr = Ys + w * kRec;
-      const double A = yr[0];
-      dS[w * 4 + 0] = A;
-      dS[w * 4 + 1] = yr[1];
-      dS[w * 4 + 2] = MERGE ? fma(Ss[c * kScal + 1] * A, A, yr[2]) : yr[2];
-      dS[w * 4 + 3] = 0.0;
+      dS[w * kDerS + 0] = yr[0];
+      dS[w * kDerS + 1] = yr[1];
+      dS[w * kDerS + 2] = yr[2];
+      dS[w * kDerS + 3] = 0.0;
     }
 #pragma unroll 1
     for (int w = threadIdx.x; w < CT * NPT; w += nthreads) {
-      const int c = w / NPT;
       const double *pr = Ps + w * kRec;
-      const double B = pr[0];
-      dP[w * 4 + 0] = B;
-      dP[w * 4 + 1] = pr[1];
-      dP[w * 4 + 2] = MERGE ? fma(Ss[c * kScal + 1] * B, B, pr[2]) : pr[2];
-      dP[w * 4 + 3] = 0.0;
+      const double q = pT * pr[0];
+      double fq; int fm;
+      exp_neg_poly(-q, fq, fm);                                    // e^{+q} = fq 2^fm
+      dP[w * kDerP + 0] = q;
+      dP[w * kDerP + 1] = pT * pr[1];
+      dP[w * kDerP + 2] = pT2 * pr[2];
+      dP[w * kDerP + 3] = fq;
+      *reinterpret_cast<int2 *>(dP + w * kDerP + 4) = make_int2(fm, 0);
+      dP[w * kDerP + 5] = 0.0;
     }
-    if (MODEL != M_IDEAL) {
+    if (POLY) {
 #pragma unroll 1
       for (int w = threadIdx.x; w < CT * NYT * NPT; w += nthreads) {
         const int c = w / (NYT * NPT), r = w - c * (NYT * NPT), j = r / NPT, k = r - j * NPT;
         const double *yr = Ys + (c * NYT + j) * kRec, *pr = Ps + (c * NPT + k) * kRec;
-        double v = fma(pr[4], yr[4], -(pr[3] * yr[3]));                          // R2 U2 - R1 U1
-        if (MERGE) v = fma(-2.0 * Ss[c * kScal + 1] * yr[0], pr[0], v);          // - 2 K2 A B
-        dX[(c * NYT + j) * PP + k] = v;
+        dX[(c * NYT + j) * PP + k] = pT * fma(pr[4], yr[4], -(pr[3] * yr[3]));
       }
     }
 #pragma unroll 1
     for (int c = threadIdx.x; c < CT; c += nthreads) {
       double bmax = Ps[c * NPT * kRec], babs = fabs(bmax);
       for (int k = 1; k < NPT; k++) { const double b = Ps[(c * NPT + k) * kRec]; bmax = fmax(bmax, b); babs = fmax(babs, fabs(b)); }
+      bool live = false;                                 // any slot of this cell that is not a dead record (padding, skipped cell,
+      for (int j = 0; j < NYT; j++) live = live || Ys[(c * NYT + j) * kRec] < 0.5 * kDeadSlotA;   // slot owned by the other record set)
+      const bool general = !(babs * pT <= kQLimit);
       dC[c * kDerC + 0] = Ss[c * kScal + 0];
       dC[c * kDerC + 1] = Ss[c * kScal + 1];
       dC[c * kDerC + 2] = 1.0 + Ss[c * kScal + 2];
-      dC[c * kDerC + 3] = bmax;
-      bool live = false;                                 // any slot of this cell that is not a dead record (padding, skipped cell,
-      for (int j = 0; j < NYT; j++) live = live || Ys[(c * NYT + j) * kRec] < 0.5 * kDeadSlotA;   // slot owned by the other record set)
-      *reinterpret_cast<int2 *>(dC + c * kDerC + 4) = make_int2((babs * hp.pT_max <= kQLimit) ? 0 : 1, live ? 0 : 1);
-      dC[c * kDerC + 5] = 0.0;
+      // a slot is dead when mT A > ln(DBL_MAX) + max_k pT B[k]; compared on the high words, so the sliver in between stays alive
+      const int dead_hi = !live ? (int)0x80000000 : general ? 0x7fffffff : __double2hiint(fma(pT, bmax, 709.79));
+      *reinterpret_cast<int2 *>(dC + c * kDerC + 3) = make_int2(dead_hi, general ? 1 : 0);
+      dC[c * kDerC + 4] = 0.0; dC[c * kDerC + 5] = 0.0;
     }
     __syncthreads();                                   // tables of tile t complete; every warp is past the inner loop of tile t - 1
     if (threadIdx.x == 0 && t + kStages < n_my_tiles) issue(t + kStages);     // stage st has been consumed by the derive pass
 
     for (int c = 0; c < CT; c++) {
+      const int2 flg = *reinterpret_cast<const int2 *>(dC + c * kDerC + 3);
+      const int dead_hi = flg.x;
+      if (dead_hi == (int)0x80000000) continue;          // nothing alive in this cell (block-uniform)
+      const bool cell_general = flg.y != 0;
       const double2 k01 = *reinterpret_cast<const double2 *>(dC + c * kDerC);
-      const double2 k23 = *reinterpret_cast<const double2 *>(dC + c * kDerC + 2);
-      const int2 flg = *reinterpret_cast<const int2 *>(dC + c * kDerC + 4);        // general-path flag, dead-cell flag
-      if (flg.y != 0) continue;                         // nothing alive in this cell
-      const bool cell_general = flg.x != 0;
       const double K0m = k01.x * m2;
-      const double K2 = k01.y;                          // Chapman-Enskog / Jonah: coefficient of x
-      const double K31 = k23.x;                         // 1 + K3 (Jonah), 1 otherwise
-      // dead test of a slot: mT A > ln(DBL_MAX) + max_k pT B[k] (compared on the high words, so the sliver in between goes
-      // through the exact path)
-      const int dead_hi = cell_general ? 0x7fffffff : __double2hiint(fma(pT, k23.y, 709.79));
+      const double K2 = k01.y;
+      const double K31 = dC[c * kDerC + 2];
 
-      double fq[NPT], pd[NPT], G[NPT], q[NEEDX ? NPT : 1]; int fm[NPT];
+      double q[NPT], pd[NPT], G0[NPT], fq[NPT]; int fm[NPT];
 #pragma unroll
       for (int k = 0; k < NPT; k++) {
-        const double2 v0 = *reinterpret_cast<const double2 *>(dP + (c * NPT + k) * 4);
-        const double qpp = dP[(c * NPT + k) * 4 + 2];
-        const double qk = pT * v0.x;                    // pT (cos ux + sin uy) / T
-        if (NEEDX) q[k] = qk;
-        pd[k] = pT * v0.y;                              // pT (cos dsigma_x + sin dsigma_y)
-        G[k] = fma(pT2, qpp, K0m);                      // pT^2 Qpp' + K0 m^2
-        exp_neg_poly(-qk, fq[k], fm[k]);                // e^{+q} = fq 2^fm
+        const double2 v0 = *reinterpret_cast<const double2 *>(dP + (c * NPT + k) * kDerP);
+        const double2 v1 = *reinterpret_cast<const double2 *>(dP + (c * NPT + k) * kDerP + 2);
+        q[k] = v0.x; pd[k] = v0.y; G0[k] = v1.x; fq[k] = v1.y;
+        fm[k] = *reinterpret_cast<const int *>(dP + (c * NPT + k) * kDerP + 4);
       }
 
 #pragma unroll
       for (int j = 0; j < NYT; j++) {
-        const double2 s0 = *reinterpret_cast<const double2 *>(dS + (c * NYT + j) * 4);
+        const double2 s0 = *reinterpret_cast<const double2 *>(dS + (c * NYT + j) * kDerS);
         const double a = mT * s0.x;                     // mT A: the slot part of u.p / T
-        if (__double2hiint(a) > dead_hi) continue;      // every member dead: exact 0
+        const bool pre_dead = __double2hiint(a) > dead_hi;
+        if (__all_sync(kFull, pre_dead)) continue;      // every member of every lane dead: exact 0
         double *accj = acc + j * NPT;
-        const double qyy = dS[(c * NYT + j) * 4 + 2];
         const double *xr = dX + (c * NYT + j) * PP;
-        const double cpm = mT * s0.y;                   // mT (cosh dsigma_tau + sinh dsigma_eta / tau)
         double pe; int ne;
-        exp_neg_poly(a, pe, ne);                        // e^{-a} = pe 2^ne
+        exp_neg_poly(a, pe, ne);                        // e^{-a} = pe 2^ne (garbage for pre_dead lanes, which are forced dead)
+        if (pre_dead) ne = kNForcedDead;
         int n[NPT], nmin, nmax;
 #pragma unroll
         for (int k = 0; k < NPT; k++) n[k] = ne + fm[k];
         nmin = n[0]; nmax = n[0];
 #pragma unroll
         for (int k = 1; k < NPT; k++) { nmin = min(nmin, n[k]); nmax = max(nmax, n[k]); }
-        if (nmax <= kNDead && !cell_general) continue;
-        const double H = mT2 * qyy;                     // mT^2 Qyy'
+        const bool dead_t = (nmax <= kNDead && !cell_general) || pre_dead;
+        const bool ok_t = nmin >= kNNormal && !cell_general;           // every member alive with a normal e^{-x}: fast path
+        const bool late_t = !dead_t && !ok_t;                           // some member dead / sub-normal / out of range
+        const bool dil_w = __all_sync(kFull, !ok_t || nmax <= kNDilute);
+        const bool ult_w = __all_sync(kFull, !ok_t || nmax <= kNUltra);
+        const double cpm = mT * s0.y;                   // mT (cosh dsigma_tau + sinh dsigma_eta / tau)
+        const double H = POLY ? fma(mT2, dS[(c * NYT + j) * kDerS + 2], K0m) : 0.0;     // mT^2 Qyy + K0 m^2
+        double pv[NPT];
+#pragma unroll
+        for (int k = 0; k < NPT; k++) pv[k] = pd[k] + cpm;              // p.dsigma
+        int pvlo = __double2hiint(pv[0]);
+#pragma unroll
+        for (int k = 1; k < NPT; k++) pvlo = min(pvlo, __double2hiint(pv[k]));
+        const bool pos_w = __all_sync(kFull, !ok_t || pvlo > thr_hi);   // outflow test passes for every member of every fast lane
 
-        if (__builtin_expect(nmin >= kNNormal && !cell_general, 1)) {
-          // ---------------- fast paths: every member alive with a normal e^{-x}
+        if (ok_t) {
           double av[NPT], g[NPT], fe[NPT];
 #pragma unroll
           for (int k = 0; k < NPT; k++) {
             const double pm = pe * fq[k];
             av[k] = __hiloint2double(__double2hiint(pm) + (n[k] << 20), __double2loint(pm));
           }
-          if (MODEL == M_IDEAL) {
-            if (nmax <= kNUltra) {
+          if (POLY) {
 #pragma unroll
-              for (int k = 0; k < NPT; k++) fe[k] = av[k];
-            } else if (nmax <= kNDilute) {
-#pragma unroll
-              for (int k = 0; k < NPT; k++) fe[k] = av[k] * fma(av[k], av[k], fma(nsign, av[k], 1.0));
-            } else {
-#pragma unroll
-              for (int k = 0; k < NPT; k++) fe[k] = av[k] * rcp_fast(fma(sign, av[k], 1.0));
-            }
-            accumulate_group<NPT>(accj, pd, cpm, fe, nullptr, thr_hi);
-            continue;
+            for (int k = 0; k < NPT; k++) g[k] = df_poly<MODEL>(fma(mT, xr[k], H + G0[k]), a - q[k], K2);
           }
-          // delta-f polynomial (without feqbar)
-          double dfs[NPT];
+          if (ult_w) {                                  // feqbar = 1 exactly
 #pragma unroll
-          for (int k = 0; k < NPT; k++) {
-            const double s = fma(mTpT, xr[k], H + G[k]);
-            if (NEEDX) {
-              const double x = a - q[k];
-              dfs[k] = fma(s, rcp_fast(x), K2 * x);     // [..] / (u.p) + (..) (u.p)
-            } else dfs[k] = s;
-          }
-          if (nmax <= kNUltra) {                        // feqbar = 1 exactly
-#pragma unroll
-            for (int k = 0; k < NPT; k++) { g[k] = dfs[k] + K31; fe[k] = av[k]; }
-          } else if (nmax <= kNDilute) {
+            for (int k = 0; k < NPT; k++) { fe[k] = av[k]; if (POLY) g[k] = g[k] + K31; }
+          } else if (dil_w) {
 #pragma unroll
             for (int k = 0; k < NPT; k++) {
               const double fb = fma(av[k], av[k], fma(nsign, av[k], 1.0));
-              g[k] = fma(fb, dfs[k], K31); fe[k] = av[k] * fb;
+              fe[k] = av[k] * fb; if (POLY) g[k] = fma(fb, g[k], K31);
             }
           } else {
 #pragma unroll
             for (int k = 0; k < NPT; k++) {
               const double fb = rcp_fast(fma(sign, av[k], 1.0));
-              g[k] = fma(fb, dfs[k], K31); fe[k] = av[k] * fb;
+              fe[k] = av[k] * fb; if (POLY) g[k] = fma(fb, g[k], K31);
             }
           }
-          unsigned hmax = (unsigned)__double2hiint(g[0]);
+          if (POLY) {
 #pragma unroll
-          for (int k = 1; k < NPT; k++) hmax = max(hmax, (unsigned)__double2hiint(g[k]));
-          if (hmax > hp.reg_chk) {
-#pragma unroll
-            for (int k = 0; k < NPT; k++) g[k] = clamp_g(g[k], reg_lo, reg_hi);
+            for (int k = 0; k < NPT; k++) fe[k] *= clamp_g(g[k], reg_lo, reg_hi);
           }
-          accumulate_group<NPT>(accj, pd, cpm, fe, g, thr_hi);
-        } else {
-          // ---------------- general path: some member is dead, sub-normal, or the cell's factors are out of range; per member
-          //                  exactly as cf_kernels.cu decides it (x itself, exp_neg_slow)
+          if (pos_w) {
+#pragma unroll
+            for (int k = 0; k < NPT; k++) accj[k] = fma(pv[k], fe[k], accj[k]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < NPT; k++) accumulate_pos(accj[k], pv[k], fe[k], thr_hi);
+          }
+        }
+        if (late_t) {
 #pragma unroll
           for (int k = 0; k < NPT; k++) {
-            const double x = a - (NEEDX ? q[k] : pT * dP[(c * NPT + k) * 4]);      // the same a - fl(pT B) as everywhere else
-            double avk;
-            if (cell_general) avk = exp_finite(x) ? exp_neg(x) : 0.0;
-            else avk = exp_neg_slow(x, pe * fq[k], n[k]);
-            const double fb = rcp_fast(fma(sign, avk, 1.0));
-            const double fe1 = avk * fb;
-            double g1 = 1.0;
-            if (MODEL != M_IDEAL) {
-              const double s = fma(mTpT, xr[k], H + G[k]);
-              const double d = NEEDX ? fma(s, rcp_fast(x), K2 * x) : s;
-              g1 = clamp_g(fma(fb, d, K31), reg_lo, reg_hi);
-            }
-            accumulate_pos(accj[k], pd[k] + cpm, fe1 * g1, thr_hi);
+            const double sk = POLY ? fma(mT, xr[k], H + G0[k]) : 0.0;
+            accj[k] += late_member<MODEL>(a - q[k], sk, pv[k], K2, K31, sign, reg_lo, reg_hi, thr_hi);
           }
         }
       }
@@ -332,17 +316,18 @@ cf_factored_kernel(const HotParams hp)
   }
 
   __syncthreads();                                     // the stage area becomes the epilogue's scratch
-  hot_epilogue<NYT, NPT, false>(hp, acc, stage_base, chunk, gb, ty, tp, lane_valid, ipart, ipT);
+  hot_epilogue<NYT, NPT, false>(hp, acc, stage_base, chunk, sb, ty, tp, lane_valid, ipart, ipT);
 }
 
 // ------------------------------------------------------------------------------------------------ dispatch
 // Register-tile shapes of the factored kernel; is3d_options.tile_variant = 17 + k selects entry k.
-struct FShape { int nyt, npt, ct, minb; };
-static const FShape kFShapes[kNumFactoredVariants] = {{7, 3, 8, 3}, {7, 4, 8, 3}, {7, 3, 8, 4}, {7, 6, 8, 2}};
+struct FShape { int nyt, npt, ct, minb, warps; };
+static const FShape kFShapes[kNumFactoredVariants] = {{7, 3, 8, 3, 4}, {7, 4, 8, 3, 4}, {7, 3, 8, 6, 2}, {7, 6, 8, 2, 4}};
 
 bool factored_supported(int model, const Layout &L)
 {
-  return !L.dim2 && (model == M_LIN14 || model == M_LINCE || model == M_JONAHLIN || model == M_IDEAL);
+  return !L.dim2 && L.n_species >= kFactoredMinSpecies &&
+         (model == M_LIN14 || model == M_LINCE || model == M_JONAHLIN || model == M_IDEAL);
 }
 
 int factored_match(int nyt, int npt)
@@ -356,20 +341,36 @@ void factored_variant_shape(int fvariant, int *nyt, int *npt, int *ct, int *max_
 {
   if (fvariant < 0 || fvariant >= kNumFactoredVariants) fvariant = 0;
   const FShape &s = kFShapes[fvariant];
-  *nyt = s.nyt; *npt = s.npt; *ct = s.ct; *max_warps = kMaxWarps;
+  *nyt = s.nyt; *npt = s.npt; *ct = s.ct; *max_warps = s.warps;
 }
 
-template <int MODEL, int NYT, int NPT, int MINB>
+// lanes are species: blocks of n_warps x 32 species, one block column per pT point
+void factored_blocking(int fvariant, int n_species, int n_pT, int *n_warps, int *n_groupblocks)
+{
+  if (fvariant < 0 || fvariant >= kNumFactoredVariants) fvariant = 0;
+  const int max_warps = kFShapes[fvariant].warps;
+  const int n_groups = (n_species + 31) / 32;
+  int best_w = 1, best = 1 << 30;
+  for (int w = max_warps; w >= 1; w--) {                 // widest block that launches the fewest warps
+    const int launched = ((n_groups + w - 1) / w) * w;
+    if (launched < best) { best = launched; best_w = w; }
+  }
+  *n_warps = best_w;
+  *n_groupblocks = ((n_groups + best_w - 1) / best_w) * n_pT;
+}
+
+template <int MODEL, int NYT, int NPT, int WARPS, int MINB>
 static cudaError_t launch_f(const HotParams &hp, cudaStream_t st, size_t *smem_out)
 {
   const Layout &L = hp.L;
   constexpr int PP = PairPitch<NPT>::v;
   const size_t stage_doubles = (size_t)L.ct * (NYT * kRec + NPT * kRec + kScal);
-  const size_t der_doubles = (size_t)L.ct * (NYT * 4 + NPT * 4 + kDerC + NYT * PP);
-  size_t smem = (kStages * stage_doubles + 2 * der_doubles) * 8 + kStages * sizeof(uint64_t);
-  smem = std::max(smem, hot_epilogue_scratch_bytes(hp, NYT, false, hp.n_warps * 32));
+  const size_t der_doubles = (size_t)L.ct * (NYT * kDerS + NPT * kDerP + kDerC + NYT * PP);
+  const size_t smem = (kStages * stage_doubles + 2 * der_doubles) * 8 + kStages * sizeof(uint64_t);
   if (smem_out) *smem_out = smem;
-  auto kern = cf_factored_kernel<MODEL, NYT, NPT, MINB>;
+  if (hp.integ_mode) return cudaErrorInvalidValue;       // operation = 0 integrates over the pT lanes of a block: cf_kernels.cu
+  if (hp.n_warps > WARPS) return cudaErrorInvalidValue;
+  auto kern = cf_factored_kernel<MODEL, NYT, NPT, WARPS, MINB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t grid = (int64_t)hp.n_groupblocks * L.n_ytiles * L.n_ptiles * hp.n_chunks;
@@ -382,10 +383,10 @@ template <int MODEL>
 static cudaError_t launch_fmodel(const HotParams &hp, int fvariant, cudaStream_t st, size_t *smem_out)
 {
   switch (fvariant) {
-    case 1: return launch_f<MODEL, 7, 4, 3>(hp, st, smem_out);
-    case 2: return launch_f<MODEL, 7, 3, 4>(hp, st, smem_out);
-    case 3: return launch_f<MODEL, 7, 6, 2>(hp, st, smem_out);
-    default: return launch_f<MODEL, 7, 3, 3>(hp, st, smem_out);
+    case 1: return launch_f<MODEL, 7, 4, 4, 3>(hp, st, smem_out);
+    case 2: return launch_f<MODEL, 7, 3, 2, 6>(hp, st, smem_out);
+    case 3: return launch_f<MODEL, 7, 6, 4, 2>(hp, st, smem_out);
+    default: return launch_f<MODEL, 7, 3, 4, 3>(hp, st, smem_out);
   }
 }
 

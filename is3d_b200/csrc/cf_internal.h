@@ -110,6 +110,8 @@ constexpr int kNumFactoredVariants = 4;      // shapes of cf_factored_kernel (ti
 bool factored_supported(int model, const Layout &L);
 void factored_variant_shape(int fvariant, int *nyt, int *npt, int *ct, int *max_warps);
 int factored_match(int nyt, int npt);        // factored shape with this register tile, or -1
+constexpr int kFactoredMinSpecies = 16;      // its lanes are species: shorter lists run on cf_kernel (lanes = (species, pT))
+void factored_blocking(int fvariant, int n_species, int n_pT, int *n_warps, int *n_groupblocks);
 cudaError_t launch_factored(int model, const HotParams &hp, int fvariant, cudaStream_t st, size_t *smem_out);
 // slot records of padding / skipped cells carry this A = u.p / (mT T): every evaluation is dead (exp overflows, f = 0 exactly)
 constexpr double kDeadSlotA = 1.0e6;

@@ -285,3 +285,23 @@ def run_reference(workdir, what="kernel", omp=False, threads=None, timeout=3600)
     info["breakdown"] = locals().get("bd", 0)
     info["stdout"] = r.stdout
     return np.fromfile(out), info
+
+
+def run_vah_reference(aL, Lambda_GeV, fixture=None):
+    """c0..c4 per cell from the reference's own reader (oracle/_ref/vah_ref = DeltafReader::load_coefficients of
+    src/cuda/deltafReader.cu, unmodified): returns an (n, 5) array in GeV units; cells outside the table keep the driver's
+    sentinel -12345 (the reference leaves them untouched)."""
+    import tempfile
+    from is3d_b200 import workdir
+    exe = os.path.join(_HERE, "_ref", "vah_ref")
+    if not os.path.exists(exe):
+        raise FileNotFoundError("oracle/_ref/vah_ref not built (run `make -C oracle ref` where /root/reference exists)")
+    aL = np.ascontiguousarray(aL, dtype=np.float64); Lam = np.ascontiguousarray(Lambda_GeV, dtype=np.float64)
+    with tempfile.TemporaryDirectory() as wd:
+        workdir.materialize(wd, fixture=fixture, vah=True, operation=1, mode=2, hrg_eos=1, dimension=3, df_mode=1)
+        with open(os.path.join(wd, "in.bin"), "wb") as f:
+            f.write(aL.tobytes()); f.write(Lam.tobytes())
+        r = subprocess.run([exe, "in.bin", "out.bin"], cwd=wd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("vah_ref failed: %s" % r.stderr[-1000:])
+        return np.fromfile(os.path.join(wd, "out.bin")).reshape(len(aL), 5)

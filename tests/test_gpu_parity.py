@@ -416,13 +416,79 @@ def test_every_tile_variant(name, fx):
         fl, cells, sp, g, _ = vah_problem(gold["recipe"], fx); tab = gla = None
     else:
         fl, cells, sp, g, tab, gla = problem_from_recipe(gold["recipe"], fx)
-    factored = name in ("s3_df1", "s3_df2")            # linear-df model as the main pass on 3+1D tiles: cf_factored.cu shapes 17..20
-    for variant in range(1, 21 if factored else 17):
+    for variant in range(1, 17):
         dN, st = api.smooth_spectra(fl, cells, sp, g, tab, gla, tile_variant=variant)
         assert st["tile_variant"] == variant - 1
         rep = compare(dN, gold["dN"])
         assert rep["ok"], (name, variant, rep)
-    if not factored:
-        with pytest.raises(api.Is3dError) as e:
-            api.smooth_spectra(fl, cells, sp, g, tab, gla, tile_variant=17)
-        assert e.value.code == 1
+    with pytest.raises(api.Is3dError) as e:                  # the factored kernel's lanes are species: needs >= 16 of them
+        api.smooth_spectra(fl, cells, sp, g, tab, gla, tile_variant=17)
+    assert e.value.code == 1
+
+
+# ---------------------------------------------------------------------------------------- factored kernel (cf_factored.cu)
+def _mid_species(fx, n):
+    ids = fx["chosen_urqmd"]
+    return tables.species(fx, 1, list(ids[:: max(1, len(ids) // n)][:n]))
+
+
+@pytest.mark.parametrize("case", ["df1", "df2", "ideal", "df1_noreg", "df2_noreg", "df1_stress"])
+def test_factored_variants_against_oracle(fx, case):
+    """cf_factored_kernel (lanes = species, tile_variant 17..20; the default for >= 16 species in 3+1D) against the oracle: 45
+    species (not a multiple of the warp), 150 cells (not a multiple of the TMA tile), every shape, with and without
+    regulate_deltaf / outflow, and on the stress surface where most delta-f values are clamped"""
+    from oracle import cf_oracle as cfo
+    sp = _mid_species(fx, 45); g = tables.grid(fx); tab = tables.df_tables(fx, 1)
+    cells = synthetic.columns_to_cells(synthetic.surface_vh(150, 4242, stress=case.endswith("stress")), 1)
+    dfm = 2 if case.startswith("df2") else 1
+    extra = dict(regulate_deltaf=0, outflow=0) if case.endswith("noreg") else {}
+    if case == "ideal":
+        extra = dict(include_bulk=0, include_shear=0)
+    fl = tables.flags(df_mode=dfm, dimension=3, **extra)
+    cond = np.zeros(45 * 32 * 24 * 21)
+    ref, _, _ = cfo.smooth(fl, cells, sp, g, tab, None, conditioning=cond)
+    for variant in (0, 17, 18, 19, 20):
+        dN, st = api.smooth_spectra(fl, cells, sp, g, tab, None, tile_variant=variant)
+        assert st["tile_variant"] == (16 if variant == 0 else variant - 1)
+        rep = compare(dN, ref, conditioning=cond)
+        assert rep["ok"], (case, variant, rep, compare(dN, ref))
+    # and the (species, pT)-lane kernel on the same problem
+    dN, st = api.smooth_spectra(fl, cells, sp, g, tab, None, tile_variant=10)
+    assert compare(dN, ref, conditioning=cond)["ok"]
+
+
+def test_factored_ragged_grids_and_chunks(fx):
+    from oracle import cf_oracle as cfo
+    g0 = tables.grid(fx)
+    g = dict(g0)
+    g["pT"] = g0["pT"][:13]; g["pT_weight"] = g0["pT_weight"][:13]; g["phi"] = g0["phi"][:5]; g["phi_weight"] = g0["phi_weight"][:5]; g["y"] = g0["y"][3:12]
+    sp = _mid_species(fx, 20); tab = tables.df_tables(fx, 1)
+    for n_cells in (1, 9, 700):
+        cells = synthetic.columns_to_cells(synthetic.surface_vh(n_cells, 99 + n_cells), 1)
+        fl = tables.flags(df_mode=1, dimension=3)
+        ref, _, _ = cfo.smooth(fl, cells, sp, g, tab, None)
+        for variant, chunks in ((0, 0), (18, 1), (19, 5)):
+            dN, st = api.smooth_spectra(fl, cells, sp, g, tab, None, tile_variant=variant, n_chunks=chunks)
+            assert st["tile_variant"] >= 16
+            assert compare(dN, ref)["ok"], (n_cells, variant, chunks)
+
+
+@pytest.mark.parametrize("df_mode", [3, 4])
+def test_feqmod_breakdown_branch_on_factored_kernel(fx, df_mode):
+    """df_mode 3 / 4 on the stress surface (27 % of the cells break down) with 24 species: the linear-df second pass runs on
+    cf_factored_kernel (Chapman-Enskog / Jonah-linear models); skipped cells mixed in"""
+    from oracle import cf_oracle as cfo
+    sp = _mid_species(fx, 24); g = tables.grid(fx); tab = tables.df_tables(fx, 1); gla = tables.laguerre(fx)
+    cells = synthetic.columns_to_cells(synthetic.surface_vh(120, 777, stress=True), 1)
+    for k in ("dat", "dax", "day", "dan"):
+        cells[k][5:9] *= -1.0
+    if df_mode == 4:
+        tab.update(jonah_tables(cells, fx, 1, gla))
+    fl = tables.flags(df_mode=df_mode, dimension=3)
+    ref, skipped, bd = cfo.smooth(fl, cells, sp, g, tab, gla)
+    dN, st = api.smooth_spectra(fl, cells, sp, g, tab, gla)
+    assert st["cells_skipped_udsigma"] == skipped == 4 and st["cells_feqmod_breakdown"] == bd
+    if df_mode == 3:
+        assert bd > 10
+    rep = compare(dN, ref)
+    assert rep["ok"], rep

@@ -285,3 +285,27 @@ def test_vah_in_memory_helpers(fx):
     ref = ref_vah_cells(cols, fx)
     for k in ("aL", "Lambda", "c0", "c4"):
         assert np.allclose(mine[k], ref[k], rtol=1e-12, atol=0), k
+
+
+# ---------------------------------------------------------------------------------------- anisotropic model: coefficient lookup
+def test_vah_coefficients_pinned_to_reference_reader(fx):
+    """the (Lambda, alpha_L) -> c0..c4 lookup against the reference's ONLY reader of these tables,
+    DeltafReader::load_coefficients (src/cuda/deltafReader.cu:192-277), compiled unmodified into oracle/_ref/vah_ref.
+    Vectors: tests/golden/vah_coefficients.npz (make_vah_coeff_vectors.py); where oracle/_ref/vah_ref exists it is re-run live."""
+    from is3d_b200 import api
+    from oracle import cf_oracle as cfo
+    from common import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "vah_coefficients.npz"))
+    aL, Lam, ref = z["aL"], z["Lambda_GeV"], z["c"]
+    if os.path.exists(os.path.join(os.path.dirname(cfo.__file__), "_ref", "vah_ref")):
+        assert np.array_equal(cfo.run_vah_reference(aL, Lam, fx), ref)                    # the fixture is what the reference computes
+    inside = ref[:, 0] != -12345.0                                                           # the reference leaves other cells untouched
+    assert 0.9 < inside.mean() < 1.0
+    got = api.vah_coefficients(fx, Lam[inside], aL[inside])
+    for k in range(5):
+        assert np.array_equal(got[k], ref[inside, k]), k                                     # bit-exact: same arithmetic, same order
+    # the test-suite's own numpy restatement (tests/common.py vah_cells) agrees as well
+    for i in np.flatnonzero(~inside)[:12]:                                                   # outside the table: an error, not garbage
+        with pytest.raises(api.Is3dError) as e:
+            api.vah_coefficients(fx, Lam[i:i + 1], aL[i:i + 1])
+        assert e.value.code == 3
