@@ -245,12 +245,12 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   if (iq && iq->mode == 2 && !dim2) return fail(IS3D_ERR_ARGUMENT, "per-slot integration is a 2+1D pass");
   if (iq && (!iq->pT_weight || !iq->phi_weight)) return fail(IS3D_ERR_ARGUMENT, "pT / phi quadrature weights missing");
   // tile_variant: 0 = model default (tuned on B200, see profiles/), k > 0 = table entry k - 1 (tuning / tests)
-  // 17..20 = shapes of the factored kernel (cf_factored.cu; linear-df models on 3+1D tiles), the default where it applies
+  // 17..21 = shapes of the factored kernel (cf_factored.cu; linear-df models on 3+1D tiles), the default where it applies
   int variant, fvariant = -1;
   const bool f_ok = factored_supported(model, L) && !iq;      // operation = 0 integrates over the pT lanes of a block (cf_kernel)
   if (opt.tile_variant >= 1 && opt.tile_variant <= kNumVariants) variant = opt.tile_variant - 1;
   else if (opt.tile_variant > kNumVariants && opt.tile_variant <= kNumVariants + kNumFactoredVariants) {
-    if (!f_ok) return fail(IS3D_ERR_ARGUMENT, "tile_variant 17..20 (factored kernel) needs df_mode 1/2, dimension 3, operation 1 and >= 16 species");
+    if (!f_ok) return fail(IS3D_ERR_ARGUMENT, "tile_variant 17..21 (factored kernel) needs df_mode 1/2, dimension 3, operation 1 and >= 16 species");
     variant = opt.tile_variant - 1; fvariant = variant - kNumVariants;
   }
   else if (f_ok) { fvariant = 0; variant = kNumVariants + fvariant; }
@@ -302,8 +302,8 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
     }
   }
   int n_groupblocks = (n_groups + n_warps - 1) / n_warps;
-  if (fvariant >= 0) factored_blocking(fvariant, sp->n, gr->n_pT, &n_warps, &n_groupblocks);     // lanes = species, one block column per pT
-  const int64_t n_bintiles = (int64_t)n_groupblocks * L.n_ytiles * L.n_ptiles;
+  if (fvariant >= 0) factored_blocking(sp->n, gr->n_pT, L.n_ptiles, &n_warps, &n_groupblocks);   // lanes = species, warps = phi tiles
+  const int64_t n_bintiles = (int64_t)n_groupblocks * L.n_ytiles * (fvariant >= 0 ? 1 : L.n_ptiles);      // blocks per cell chunk
   int n_chunks = opt.n_chunks;
   if (n_chunks <= 0) {
     const int64_t target_blocks = (int64_t)g_sm_count * 96;             // >= 16 waves at 6 blocks/SM: small tail
@@ -526,8 +526,8 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
       const int lin_model = fl->df_mode == 3 ? M_LINCE : M_JONAHLIN;
       const int lin_f = (factored_supported(lin_model, L) && !iq) ? factored_match(nyt, npt) : -1;
       if (lin_f >= 0) {
-        factored_blocking(lin_f, sp->n, gr->n_pT, &hl.n_warps, &hl.n_groupblocks);
-        if ((int64_t)hl.n_groupblocks * L.n_ytiles * L.n_ptiles * n_chunks > 2147483647LL) return fail(IS3D_ERR_ARGUMENT, "grid too large");
+        factored_blocking(sp->n, gr->n_pT, L.n_ptiles, &hl.n_warps, &hl.n_groupblocks);
+        if ((int64_t)hl.n_groupblocks * L.n_ytiles * n_chunks > 2147483647LL) return fail(IS3D_ERR_ARGUMENT, "grid too large");
         CU_CHECK(launch_factored(lin_model, hl, lin_f, st, nullptr));
       }
       else CU_CHECK(launch_hot(lin_model, hl, variant, st, nullptr));

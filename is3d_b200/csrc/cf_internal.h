@@ -106,12 +106,13 @@ cudaError_t launch_fp64_peak(double *sink, int iters, cudaStream_t st, int *bloc
 void hot_variant_shape(int variant, int dim2, int *nyt, int *npt, int *ct, int *max_warps);
 // factored kernel (cf_factored.cu): linear-df models, 3+1D tiles only
 constexpr int kNumVariants = 16;             // register-tile variants of cf_kernel (is3d_options.tile_variant 1..16)
-constexpr int kNumFactoredVariants = 4;      // shapes of cf_factored_kernel (tile_variant 17..20)
+constexpr int kNumFactoredVariants = 5;      // shapes of cf_factored_kernel (tile_variant 17..21)
 bool factored_supported(int model, const Layout &L);
 void factored_variant_shape(int fvariant, int *nyt, int *npt, int *ct, int *max_warps);
 int factored_match(int nyt, int npt);        // factored shape with this register tile, or -1
 constexpr int kFactoredMinSpecies = 16;      // its lanes are species: shorter lists run on cf_kernel (lanes = (species, pT))
-void factored_blocking(int fvariant, int n_species, int n_pT, int *n_warps, int *n_groupblocks);
+// warps = phi tiles of a block; n_groupblocks = blocks per (cell chunk, y tile) = species groups x pT points x phi blocks
+void factored_blocking(int n_species, int n_pT, int n_ptiles, int *n_warps, int *n_groupblocks);
 cudaError_t launch_factored(int model, const HotParams &hp, int fvariant, cudaStream_t st, size_t *smem_out);
 // slot records of padding / skipped cells carry this A = u.p / (mT T): every evaluation is dead (exp overflows, f = 0 exactly)
 constexpr double kDeadSlotA = 1.0e6;

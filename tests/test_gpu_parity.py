@@ -434,7 +434,7 @@ def _mid_species(fx, n):
 
 @pytest.mark.parametrize("case", ["df1", "df2", "ideal", "df1_noreg", "df2_noreg", "df1_stress"])
 def test_factored_variants_against_oracle(fx, case):
-    """cf_factored_kernel (lanes = species, tile_variant 17..20; the default for >= 16 species in 3+1D) against the oracle: 45
+    """cf_factored_kernel (lanes = species, tile_variant 17..21; the default for >= 16 species in 3+1D) against the oracle: 45
     species (not a multiple of the warp), 150 cells (not a multiple of the TMA tile), every shape, with and without
     regulate_deltaf / outflow, and on the stress surface where most delta-f values are clamped"""
     from oracle import cf_oracle as cfo
@@ -447,7 +447,7 @@ def test_factored_variants_against_oracle(fx, case):
     fl = tables.flags(df_mode=dfm, dimension=3, **extra)
     cond = np.zeros(45 * 32 * 24 * 21)
     ref, _, _ = cfo.smooth(fl, cells, sp, g, tab, None, conditioning=cond)
-    for variant in (0, 17, 18, 19, 20):
+    for variant in (0, 17, 18, 19, 20, 21):
         dN, st = api.smooth_spectra(fl, cells, sp, g, tab, None, tile_variant=variant)
         assert st["tile_variant"] == (16 if variant == 0 else variant - 1)
         rep = compare(dN, ref, conditioning=cond)
