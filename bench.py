@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--single-process", action="store_true",
+                    help="--gpus N > 1 without torchrun: ONE process drives N GPUs through is3d_b200_smooth_spectra_multi "
+                         "(cells sharded and all-reduced inside the C ABI, host arrays in and out)")
     return ap.parse_args()
 
 
@@ -192,6 +195,115 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+
+# ------------------------------------------------------------------------------------------------ roofline helpers
+# FP64-pipe instructions executed per evaluation (warp instructions per warp-evaluation, dead evaluations included), from the
+# committed ncu captures of the default kernel of each model (profiles/README.md names the file behind every number)
+FP64_INSTR_PER_EVAL = {1: 17.76, 2: 21.9, 3: 22.6, 4: 22.6, 5: 21.0, "ideal2d": 9.4}
+
+
+def alive_fraction(cells, sp, g, dim, n_sample=256, vah=False):
+    """Fraction of the evaluations whose exp(u.p / T) stays finite in the reference (the others are exactly 0 there and are skipped
+    by the kernels), counted on a random sample of cells with torch on the GPU: x = (p.u) / T <= ln(DBL_MAX)."""
+    import torch
+    n = len(cells["tau"])
+    idx = np.random.default_rng(7).choice(n, size=min(n_sample, n), replace=False)
+    dev = "cuda"
+    t = lambda k: torch.from_numpy(np.ascontiguousarray(np.asarray(cells[k])[idx])).to(dev)
+    tau, eta, ux, uy, un = t("tau"), t("eta"), t("ux"), t("uy"), t("un")
+    T = t("Lambda") if vah else t("T")
+    ut = torch.sqrt(1.0 + ux * ux + uy * uy + tau * tau * un * un)
+    mass = torch.from_numpy(np.asarray(sp["mass"])).to(dev); pT = torch.from_numpy(np.asarray(g["pT"])).to(dev)
+    phi = torch.from_numpy(np.asarray(g["phi"])).to(dev)
+    if dim == 3:
+        yv = torch.from_numpy(np.asarray(g["y"])).to(dev)
+        d = yv[None, :] - eta[:, None]
+    else:
+        d = -torch.from_numpy(np.asarray(g["eta"])).to(dev)[None, :].expand(len(idx), -1)
+    A = (torch.cosh(d) * ut[:, None] - tau[:, None] * torch.sinh(d) * un[:, None]) / T[:, None]          # [cell, slot]
+    B = (torch.cos(phi)[None, :] * ux[:, None] + torch.sin(phi)[None, :] * uy[:, None]) / T[:, None]      # [cell, phi]
+    mT = torch.sqrt(mass[:, None] ** 2 + pT[None, :] ** 2)                                               # [species, pT]
+    alive = 0; total = 0
+    for c0 in range(0, len(idx), 8):
+        a = A[c0:c0 + 8, None, None, :, None] * mT[None, :, :, None, None]                                # cell, species, pT, slot, phi
+        x = a - (pT[None, None, :, None, None] * B[c0:c0 + 8, None, None, None, :])
+        alive += int((x <= 709.782712893384).sum().item()); total += x.numel()
+    return alive / total
+
+
+def _measured_traffic(workload, operation):
+    """dram__bytes_read + dram__bytes_write of one full-size launch of the dominant kernel (ncu --set full), if a capture of this
+    workload is committed under profiles/ (r2_traffic.json: {workload: bytes})."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        return d.get("%s_op%d" % (workload, operation))
+    except Exception:
+        return None
+
+
+def run_single_process(args):
+    """--gpus N --single-process: ONE process, N GPUs, through is3d_b200_smooth_spectra_multi (host arrays; cells sharded by the C
+    ABI over one host thread + stream per device, one ncclAllReduce of the spectra).  Every number is end to end by construction."""
+    import torch
+    from is3d_b200 import api, synthetic, tables
+    n_full, dim, dfm, chosen, viscous, desc = WORKLOADS[args.workload]
+    if dfm == 5 or args.operation == 0:
+        raise SystemExit("--single-process covers the operation = 1 viscous-hydro workloads")
+    n_cells = args.cells or n_full
+    n_dev = api.init_devices(args.gpus)
+    if n_dev != args.gpus:
+        raise SystemExit("asked for %d GPUs, library initialised %d" % (args.gpus, n_dev))
+    fx = tables.load_fixture()
+    sp = tables.species(fx, 1, chosen); g = tables.grid(fx); tab = tables.df_tables(fx, 1); gla = tables.laguerre(fx)
+    fl = tables.flags(df_mode=dfm, dimension=dim, include_bulk=int(viscous), include_shear=int(viscous))
+    cells = synthetic.columns_to_cells(synthetic.surface_vh(n_cells, synthetic.SEEDS["cfg3" if dim == 3 else "cfg2"], three_d=(dim == 3), viscous=viscous), 1)
+    if dfm == 4:
+        pdg = tables.pdg_table(fx, 1)
+        tab.update(api.jonah_tables(pdg["mass"], pdg["gspin"].astype(float), pdg["sign"].astype(float), api.surface_averages(cells)[0], gla))
+    keys = ["tau", "eta", "dat", "dax", "day", "dan", "ux", "uy", "un", "T", "P", "E", "pixx", "pixy", "pixn", "piyy", "piyn", "bulkPi"]
+    host = {k: torch.from_numpy(np.ascontiguousarray(cells[k])).pin_memory().numpy() for k in keys}
+    n_bins = len(sp["mass"]) * len(g["pT"]) * len(g["phi"]) * len(g["y"])
+    evals_step = n_cells * len(sp["mass"]) * len(g["pT"]) * len(g["phi"]) * (len(g["y"]) if dim == 3 else len(g["eta"]))
+    out = np.zeros(n_bins)
+
+    def step():
+        out[:] = 0.0
+        _, st = api.smooth_spectra(fl, host, sp, g, tab, gla, out=out, tile_variant=args.variant, multi=True)
+        return st
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(0)
+    t0 = time.perf_counter(); sts = []
+    for _ in range(args.steps):
+        sts.append(step())
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    # the same surface on one device of the same process: bin-by-bin parity of the sharded result
+    single = np.zeros(n_bins)
+    api.smooth_spectra(fl, {k: v[:min(n_cells, 100_000)] for k, v in host.items()}, sp, g, tab, gla, out=single)
+    multi_small = np.zeros(n_bins)
+    api.smooth_spectra(fl, {k: v[:min(n_cells, 100_000)] for k, v in host.items()}, sp, g, tab, gla, out=multi_small, multi=True)
+    nz = single != 0
+    value = evals_step / (dt / args.steps)
+    line = {
+        "metric": "Cooper-Frye cell*momentum*species evaluations/s", "value": value, "unit": "evaluations/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "cells": n_cells, "species": len(sp["mass"]), "evaluations_per_step": evals_step,
+                   "mode": "single process: is3d_b200_smooth_spectra_multi, one host thread + stream per GPU, ncclAllReduce inside the C ABI; "
+                           "host arrays in, host spectra out (wall clock around the calls)",
+                   "spectra_checksum": float(out.sum())},
+        "clocks": clocks,
+        "e2e": {"value": value, "unit": "evaluations/s", "h2d_bytes_per_step": int(len(keys) * 8 * n_cells), "d2h_bytes_per_step": int(n_bins * 8)},
+        "gpu_launches": int(sum(s["gpu_launches"] for s in sts)),
+        "timing": {"kernel_ms_slowest_device": float(np.mean([s["kernel_ms"] for s in sts])), "allreduce_ms": float(np.mean([s["allreduce_ms"] for s in sts])),
+                   "h2d_ms": float(np.mean([s["h2d_ms"] for s in sts]))},
+        "multi_gpu_parity": {"cells": int(min(n_cells, 100_000)), "max_rel_err_vs_1gpu": float(np.max(np.abs(multi_small[nz] - single[nz]) / single[nz])),
+                             "zero_pattern_equal": bool(np.array_equal(single == 0, multi_small == 0))},
+    }
+    print(json.dumps(line), flush=True)
+
 # ------------------------------------------------------------------------------------------------ our arm
 def main():
     args = parse()
@@ -206,11 +318,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1 or args.gpus > 1:
-        if world != args.gpus:
-            raise SystemExit("--gpus %d needs torchrun with %d ranks (WORLD_SIZE=%d)" % (args.gpus, args.gpus, world))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    if args.single_process:
+        return run_single_process(args)
+    if world > 1 or args.gpus > 1:
+        if world != args.gpus:
+            raise SystemExit("--gpus %d needs torchrun with %d ranks (WORLD_SIZE=%d), or --single-process" % (args.gpus, args.gpus, world))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl")
@@ -349,6 +463,28 @@ def main():
                "h2d_bytes_per_step": int(len(keys) * 8 * n_cells), "d2h_bytes_per_step": int((last["flat"].size if spacetime else n_bins) * 8 * world),
                "checksum_rel_diff": abs(float(np.sum(res)) - checksum) / abs(checksum) if checksum else 0.0}
 
+    # ---- multi-GPU correctness inside the run (the driver's test box has one GPU): a reduced surface sharded over the ranks and
+    #      all-reduced, compared bin by bin on rank 0 with the same surface computed by rank 0 alone
+    multi_parity = None
+    if world > 1 and not spacetime and not vah:
+        n_small = 40_000
+        cols_s = synthetic.surface_vh(n_small, 4321, three_d=(dim == 3), viscous=viscous)
+        cells_s = synthetic.columns_to_cells(cols_s, 1)
+        lo_s, hi_s = distributed.shard_bounds(n_small, rank, world)
+        part = torch.zeros(n_bins, dtype=torch.float64, device="cuda")
+        api.smooth_spectra(fl, {k: torch.from_numpy(np.ascontiguousarray(cells_s[k][lo_s:hi_s])).cuda() for k in keys}, sp, g, tab, gla,
+                           out=part, memory="device", tile_variant=args.variant)
+        dist.all_reduce(part, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            alone = torch.zeros(n_bins, dtype=torch.float64, device="cuda")
+            api.smooth_spectra(fl, {k: torch.from_numpy(np.ascontiguousarray(cells_s[k])).cuda() for k in keys}, sp, g, tab, gla,
+                               out=alone, memory="device", tile_variant=args.variant)
+            a = alone.cpu().numpy(); b = part.cpu().numpy(); nz = a != 0
+            multi_parity = {"cells": n_small, "bins": int(a.size), "max_rel_err_vs_1gpu": float(np.max(np.abs(b[nz] - a[nz]) / np.abs(a[nz]))),
+                            "zero_pattern_equal": bool(np.array_equal(a == 0, b == 0)),
+                            "note": "sum of %d shard spectra (NCCL all-reduce) vs the same surface on rank 0 alone; differs by summation order only" % world}
+        dist.barrier()
+
     if rank != 0:
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
@@ -369,6 +505,27 @@ def main():
                         "in 169 ms = 2 GB/s, i.e. the path is not HBM-bound", "hbm_peak_gbs": _measured_hbm()},
                 "reading": "W is the reference's flop count per evaluation as written (SURVEY 8d); the restructured kernel executes ~18 FP64 "
                            "instructions per evaluation, so frac can exceed 1 -- the FP64 pipe itself is 56 % busy in the ncu capture"}
+
+    # hardware-side reading: FP64-pipe instructions actually executed per evaluation (ncu), the share of evaluations that are not
+    # identically zero in the reference, and the resulting pipe utilisation (a warp-wide FP64 instruction holds the pipe 2 cycles)
+    fkey = "ideal2d" if (dim == 2 and not viscous) else dfm
+    f64i = FP64_INSTR_PER_EVAL.get(fkey)
+    try:
+        cells_for_alive = api.vah_cells(synthetic.surface_vah(4096, synthetic.SEEDS["cfg5"]), fx) if vah else \
+            synthetic.columns_to_cells(synthetic.surface_vh(4096, synthetic.SEEDS["cfg3" if dim == 3 else "cfg2"], three_d=(dim == 3), viscous=viscous), 1)
+        alive = alive_fraction(cells_for_alive, sp, g, dim, vah=vah)
+    except Exception as e:
+        alive = None
+    evals_per_s_launch = evals_launch / (kernel_mean * 1e-3)
+    roofline.update({
+        "fp64_instr_per_eval": f64i,
+        "pipe_frac": (f64i * evals_per_s_launch / (peak_sustained * 1e12 / 2.0)) if f64i else None,
+        "alive_fraction": alive,
+        "live_evaluations_per_s": (value * alive) if alive is not None else None,
+        "traffic": _measured_traffic(args.workload, args.operation),
+        "frac_meaning": "frac = W x evaluations/s / FP64 peak with W the REFERENCE's flop count per evaluation (SURVEY 8d): a work-normalised "
+                        "speed, not a pipe utilisation; pipe_frac = executed FP64 instructions/s / (peak/2) is the hardware utilisation",
+    })
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -395,7 +552,7 @@ def main():
                    "tile_variant": args.variant, "underflow_skip": "evaluations whose exp(u.p/T) overflows (f = 0 exactly in the reference) are skipped; they still count as evaluations",
                    "spectra_checksum": checksum},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-        "fraction_of_fp64_peak": achieved / peak_sustained,
+        "fraction_of_fp64_peak": achieved / peak_sustained, "multi_gpu_parity": multi_parity,
         "timing": {"prepare_ms": sum(prepare_ms) / len(prepare_ms), "kernel_ms": kernel_mean, "reduce_ms": sum(reduce_ms) / len(reduce_ms)},
     }
     print(json.dumps(line), flush=True)

@@ -12,8 +12,10 @@
  * Further down: operation = 0 (calculate_dN_dX{,_feqmod}, smooth_kernels.cpp:1000-2135), the sampler's mean-yield pass
  * (calculate_total_yield, emissionfunction_sampling_kernels.cpp:653-831) and the file-level host layer.
  *
- * Threading: one calling host thread per process/GPU.  Multi-GPU runs use one process per GPU, each calling with its
- * own contiguous shard of cells; the caller sums the spectra arrays (one all-reduce).
+ * Threading: every entry point works on the CUDA device that is current in the calling thread and keeps one workspace per
+ * device, so different host threads may drive different devices concurrently (calls on the same device are serialised).
+ * Multi-GPU: either one process per GPU, each calling with its own contiguous shard of cells and all-reducing the spectra
+ * itself (is3d_b200/distributed.py under torchrun), or ONE process calling the *_multi entry points below.
  */
 #ifndef IS3D_B200_H
 #define IS3D_B200_H
@@ -30,7 +32,8 @@ enum {
   IS3D_ERR_TABLE_RANGE = 3,   /* a cell's T (or Pi/P for df_mode 4) lies outside the coefficient table; the reference aborts here */
   IS3D_ERR_CUDA = 4,          /* CUDA runtime failure; is3d_b200_last_error() has the text */
   IS3D_ERR_NO_DEVICE = 5,     /* no CUDA device: there is deliberately no CPU fallback */
-  IS3D_ERR_IO = 6             /* host layer: missing / malformed input file */
+  IS3D_ERR_IO = 6,            /* host layer: missing / malformed input file */
+  IS3D_ERR_NCCL = 7           /* multi-GPU: libnccl.so.2 could not be loaded, or an NCCL call failed */
 };
 
 /* Freeze-out surface, structure of arrays, GeV / fm units exactly as EmissionFunctionArray::calculate_spectra packs
@@ -99,10 +102,22 @@ typedef struct {
   double h2d_ms, prepare_ms, kernel_ms, reduce_ms, d2h_ms, total_ms;   /* CUDA-event times on the launch stream */
   int32_t gpu_launches;            /* kernels launched by this call */
   int32_t n_chunks, tile_variant;
+  int32_t n_gpus;                  /* devices that worked on this call (times above: slowest device) */
+  double allreduce_ms;             /* multi-GPU: the NCCL all-reduce of the spectra array */
 } is3d_stats;
 
-/* Bind to the current CUDA device and create the workspace.  Safe to call more than once. */
+/* Bind to the current CUDA device and create its workspace (one per CUDA ordinal).  Safe to call more than once. */
 int is3d_b200_init(void);
+/* ---- one process, several GPUs (the reference has ONE entry, IS3D::run_particlization, src/cpp/iS3D.cpp:73-191;
+ * a drop-in for it has to use the whole box by itself).  is3d_b200_init_devices(n) selects the first n visible devices (n <= 0: all
+ * of them, or the number in the environment variable IS3D_B200_GPUS) and creates one NCCL communicator over them (libnccl.so.2 is
+ * loaded at run time).  is3d_b200_smooth_spectra_multi() then takes HOST arrays, splits the cells into contiguous shards of
+ * ceil(n_cells / n) (species, grids and coefficient tables are replicated), runs one host thread and one stream per device, combines
+ * the per-device spectra with a single ncclAllReduce(sum, double) and adds device 0's copy into dN_out.  With one device it is
+ * is3d_b200_smooth_spectra().  is3d_b200_run_workdir / is3d_b200_run_surface and the IS3D class use it, so the file-level
+ * drop-in runs on every visible GPU.  Results differ from the 1-GPU result by summation order only (non-negative terms: ~1e-15). */
+int is3d_b200_init_devices(int n_gpus);
+int is3d_b200_device_count(void);     /* devices the *_multi entry points use (1 before is3d_b200_init_devices) */
 int is3d_b200_shutdown(void);
 const char *is3d_b200_strerror(int code);
 const char *is3d_b200_last_error(void);
@@ -114,6 +129,10 @@ int is3d_b200_version(void);
 int is3d_b200_smooth_spectra(const is3d_flags *flags, const is3d_surface *surface, const is3d_species *species,
                              const is3d_grid *grid, const is3d_df_tables *df, const is3d_laguerre *laguerre,
                              const is3d_options *options, double *dN_out, is3d_stats *stats);
+
+int is3d_b200_smooth_spectra_multi(const is3d_flags *flags, const is3d_surface *surface, const is3d_species *species,
+                                   const is3d_grid *grid, const is3d_df_tables *df, const is3d_laguerre *laguerre,
+                                   const is3d_options *options, double *dN_out, is3d_stats *stats);
 
 /* ---- operation = 0: spacetime distributions of the momentum-integrated yield -------------------
  * Replaces EmissionFunctionArray::calculate_dN_dX (emissionfunction_smooth_kernels.cpp:1000-1446, df_mode 1, 2) and
@@ -135,6 +154,12 @@ int is3d_b200_spacetime_distributions(const is3d_flags *flags, const is3d_surfac
                                       const is3d_grid *grid, const is3d_df_tables *df, const is3d_laguerre *laguerre,
                                       const is3d_spacetime_bins *bins, const is3d_options *options,
                                       is3d_spacetime_result *result, is3d_stats *stats);
+/* Same over the devices of is3d_b200_init_devices(): HOST arrays, contiguous cell shards, one thread per device; the histograms are
+ * linear in the cells, so the per-device raw sums (a few MB) are added on the host in device order. */
+int is3d_b200_spacetime_distributions_multi(const is3d_flags *flags, const is3d_surface *surface, const is3d_species *species,
+                                            const is3d_grid *grid, const is3d_df_tables *df, const is3d_laguerre *laguerre,
+                                            const is3d_spacetime_bins *bins, const is3d_options *options,
+                                            is3d_spacetime_result *result, is3d_stats *stats);
 
 /* FP64 FMA peak of the current device measured with a dependency-free DFMA chain (the roofline denominator;
  * MEASURED_PEAKS.json carries no FP64 figure).  Returns TFLOP/s in *tflops, SM clock not touched. */

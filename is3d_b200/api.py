@@ -19,7 +19,7 @@ SURFACE_FIELDS = ("tau", "eta", "dat", "dax", "day", "dan", "ux", "uy", "un", "T
 DF_FIELDS = ("T", "c0", "c1", "c2", "c3", "c4", "F", "G", "betabulk", "betaV", "betapi")
 
 ERRORS = {0: "IS3D_OK", 1: "IS3D_ERR_ARGUMENT", 2: "IS3D_ERR_UNSUPPORTED", 3: "IS3D_ERR_TABLE_RANGE", 4: "IS3D_ERR_CUDA",
-          5: "IS3D_ERR_NO_DEVICE", 6: "IS3D_ERR_IO"}
+          5: "IS3D_ERR_NO_DEVICE", 6: "IS3D_ERR_IO", 7: "IS3D_ERR_NCCL"}
 
 
 class Surface(C.Structure):
@@ -60,7 +60,7 @@ class Stats(C.Structure):
     _fields_ = [("cells_skipped_udsigma", C.c_int64), ("cells_feqmod_breakdown", C.c_int64), ("evaluations", C.c_int64),
                 ("h2d_ms", C.c_double), ("prepare_ms", C.c_double), ("kernel_ms", C.c_double), ("reduce_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("total_ms", C.c_double), ("gpu_launches", C.c_int32), ("n_chunks", C.c_int32),
-                ("tile_variant", C.c_int32)]
+                ("tile_variant", C.c_int32), ("n_gpus", C.c_int32), ("allreduce_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -104,6 +104,12 @@ def init():
 
 def shutdown():
     _check(lib().is3d_b200_shutdown())
+
+
+def init_devices(n_gpus=0):
+    """One process, several GPUs: select the first n_gpus visible devices (0: all / IS3D_B200_GPUS) for the *_multi entry points."""
+    _check(lib().is3d_b200_init_devices(int(n_gpus)))
+    return lib().is3d_b200_device_count()
 
 
 def measure_fp64_peak():
@@ -254,7 +260,7 @@ def _marshal_problem(m, cells, species, grid, df_tables, laguerre):
 
 
 def smooth_spectra(flags, cells, species, grid, df_tables=None, laguerre=None, out=None, memory="host",
-                   stream=None, n_chunks=0, tile_variant=0):
+                   stream=None, n_chunks=0, tile_variant=0, multi=False):
     """Call is3d_b200_smooth_spectra.
 
     cells: dict of per-cell arrays (numpy for memory='host', float64 CUDA tensors for memory='device').
@@ -281,8 +287,10 @@ def smooth_spectra(flags, cells, species, grid, df_tables=None, laguerre=None, o
     opt.stream = C.c_void_p(stream or 0); opt.n_chunks = n_chunks; opt.tile_variant = tile_variant
     st = Stats()
     fl = make_flags(flags)
-    rc = lib().is3d_b200_smooth_spectra(C.byref(fl), C.byref(sf), C.byref(sp), C.byref(g), C.byref(dft), C.byref(la),
-                                        C.byref(opt), out_ptr, C.byref(st))
+    fn = lib().is3d_b200_smooth_spectra_multi if multi else lib().is3d_b200_smooth_spectra      # multi: host arrays, all devices of init_devices()
+    fn.restype = C.c_int
+    fn.argtypes = lib().is3d_b200_smooth_spectra.argtypes
+    rc = fn(C.byref(fl), C.byref(sf), C.byref(sp), C.byref(g), C.byref(dft), C.byref(la), C.byref(opt), out_ptr, C.byref(st))
     _check(rc)
     return out, st.as_dict()
 
@@ -297,7 +305,7 @@ class SpacetimeResult(C.Structure):
 
 
 def spacetime_distributions(flags, cells, species, grid, df_tables, laguerre, bins, memory="host", stream=None,
-                            n_chunks=0, tile_variant=0):
+                            n_chunks=0, tile_variant=0, multi=False):
     """Call is3d_b200_spacetime_distributions (operation = 0).
 
     cells must also carry the transverse positions "x", "y"; grid the quadrature weights "pT_weight", "phi_weight";
@@ -325,7 +333,7 @@ def spacetime_distributions(flags, cells, species, grid, df_tables, laguerre, bi
     opt.stream = C.c_void_p(stream or 0); opt.n_chunks = n_chunks; opt.tile_variant = tile_variant
     st = Stats()
     fl = make_flags(flags)
-    f = lib().is3d_b200_spacetime_distributions
+    f = lib().is3d_b200_spacetime_distributions_multi if multi else lib().is3d_b200_spacetime_distributions
     f.restype = C.c_int
     f.argtypes = [C.POINTER(Flags), C.POINTER(Surface), C.POINTER(Species), C.POINTER(Grid), C.POINTER(DfTables),
                   C.POINTER(Laguerre), C.POINTER(SpacetimeBins), C.POINTER(Options), C.POINTER(SpacetimeResult), C.POINTER(Stats)]

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstddef>
 #include <algorithm>
 #include <mutex>
 #include <string>
@@ -12,10 +13,10 @@
 
 namespace is3d {
 
-static std::mutex g_mutex;
-static std::string g_last_error;
-static bool g_init = false;
-static int g_sm_count = 0;
+// Per-device state: one grow-only workspace, its events and a lock per CUDA ordinal.  A call works on the device that is
+// current in the calling thread; the multi-GPU entry points run one host thread per device.
+static thread_local std::string g_last_error;       // text of the calling thread's last failure
+constexpr int kMaxDevices = 64;
 
 #define CU_CHECK(call)                                                                          \
   do {                                                                                          \
@@ -56,7 +57,13 @@ struct Workspace {
     if (events) { for (auto &e : ev) cudaEventDestroy(e); events = false; }
   }
 };
-static Workspace g_ws;
+struct Device {
+  std::mutex mu;                   // one call at a time per device
+  Workspace ws;
+  int sm_count = 0;
+  bool init = false;
+};
+static Device g_dev[kMaxDevices];
 
 // bump allocator over the `small` buffer for tables; all offsets 256-byte aligned
 struct SmallArena {
@@ -83,9 +90,12 @@ struct IntegRequest {
   int n_units = 0;
 };
 
+// keep_dev != NULL: the spectra stay in the device workspace (*keep_dev receives the pointer, valid until the next call on that
+// device) instead of being added into dN_out -- used by the multi-GPU entry point, which all-reduces them first
 static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_species *sp, const is3d_grid *gr,
                        const is3d_df_tables *df, const is3d_laguerre *gla, const is3d_options *opt_in,
-                       double *dN_out, is3d_stats *stats, IntegRequest *iq);
+                       double *dN_out, is3d_stats *stats, IntegRequest *iq, double **keep_dev = nullptr);
+static void multi_shutdown();
 
 }  // namespace is3d
 
@@ -105,53 +115,78 @@ const char *is3d_b200_strerror(int code)
     case IS3D_ERR_CUDA: return "CUDA runtime error";
     case IS3D_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
     case IS3D_ERR_IO: return "input/output error in the host layer";
+    case IS3D_ERR_NCCL: return "NCCL unavailable or failed (multi-GPU entry points)";
     default: return "unknown error";
   }
 }
 
 const char *is3d_b200_last_error(void) { return g_last_error.c_str(); }
 
-int is3d_b200_init(void)
+// the calling thread's current device, initialised on first use
+static int current_device(Device **out)
 {
-  std::lock_guard<std::mutex> lk(g_mutex);
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return fail(IS3D_ERR_NO_DEVICE, "no CUDA device visible");
   int dev = 0;
   CU_CHECK(cudaGetDevice(&dev));
-  CU_CHECK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
-  if (!g_ws.events) {
-    for (auto &e : g_ws.ev) CU_CHECK(cudaEventCreate(&e));
-    g_ws.events = true;
+  if (dev < 0 || dev >= kMaxDevices) return fail(IS3D_ERR_ARGUMENT, "CUDA device ordinal out of range");
+  Device &D = g_dev[dev];
+  std::lock_guard<std::mutex> lk(D.mu);
+  if (!D.init) {
+    CU_CHECK(cudaDeviceGetAttribute(&D.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    if (!D.ws.events) {
+      for (auto &e : D.ws.ev) CU_CHECK(cudaEventCreate(&e));
+      D.ws.events = true;
+    }
+    D.init = true;
   }
-  g_init = true;
+  *out = &D;
   return IS3D_OK;
+}
+
+int is3d_b200_init(void)
+{
+  Device *D = nullptr;
+  return current_device(&D);
 }
 
 int is3d_b200_shutdown(void)
 {
-  std::lock_guard<std::mutex> lk(g_mutex);
-  g_ws.release();
-  g_init = false;
+  multi_shutdown();
+  int n = 0, prev = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return IS3D_OK;
+  cudaGetDevice(&prev);
+  for (int d = 0; d < n && d < kMaxDevices; d++) {
+    Device &D = g_dev[d];
+    std::lock_guard<std::mutex> lk(D.mu);
+    if (!D.init) continue;
+    cudaSetDevice(d);
+    D.ws.release();
+    D.init = false;
+  }
+  cudaSetDevice(prev);
   return IS3D_OK;
 }
 
 int is3d_b200_measure_fp64_peak(double *tflops, double *ms_out)
 {
-  int rc = is3d_b200_init();
+  Device *Dp = nullptr;
+  int rc = current_device(&Dp);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(g_mutex);
-  CU_CHECK(g_ws.counters.reserve(256));
+  Workspace &ws = Dp->ws;
+  std::lock_guard<std::mutex> lk(Dp->mu);
+  CU_CHECK(ws.counters.reserve(256));
   int blocks = 0, threads = 0; long long per_thread = 0;
   const int iters = 20000;
-  CU_CHECK(launch_fp64_peak(g_ws.counters.as<double>(), 2000, 0, &blocks, &threads, &per_thread));   // warm-up
+  CU_CHECK(launch_fp64_peak(ws.counters.as<double>(), 2000, 0, &blocks, &threads, &per_thread));   // warm-up
   float best = 1e30f;
   for (int rep = 0; rep < 3; rep++) {
-    CU_CHECK(cudaEventRecord(g_ws.ev[0], 0));
-    CU_CHECK(launch_fp64_peak(g_ws.counters.as<double>(), iters, 0, &blocks, &threads, &per_thread));
-    CU_CHECK(cudaEventRecord(g_ws.ev[1], 0));
-    CU_CHECK(cudaEventSynchronize(g_ws.ev[1]));
+    CU_CHECK(cudaEventRecord(ws.ev[0], 0));
+    CU_CHECK(launch_fp64_peak(ws.counters.as<double>(), iters, 0, &blocks, &threads, &per_thread));
+    CU_CHECK(cudaEventRecord(ws.ev[1], 0));
+    CU_CHECK(cudaEventSynchronize(ws.ev[1]));
     float ms = 0;
-    CU_CHECK(cudaEventElapsedTime(&ms, g_ws.ev[0], g_ws.ev[1]));
+    CU_CHECK(cudaEventElapsedTime(&ms, ws.ev[0], ws.ev[1]));
     if (ms < best) best = ms;
   }
   const double flops = 2.0 * (double)per_thread * blocks * threads;
@@ -162,21 +197,23 @@ int is3d_b200_measure_fp64_peak(double *tflops, double *ms_out)
 
 int is3d_b200_measure_fp64_sustained(double seconds, double *tflops)
 {
-  int rc = is3d_b200_init();
+  Device *Dp = nullptr;
+  int rc = current_device(&Dp);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(g_mutex);
-  CU_CHECK(g_ws.counters.reserve(256));
+  Workspace &ws = Dp->ws;
+  std::lock_guard<std::mutex> lk(Dp->mu);
+  CU_CHECK(ws.counters.reserve(256));
   int blocks = 0, threads = 0; long long per_thread = 0;
   const int iters = 20000;                       // ~21 ms per launch at the burst clock
-  CU_CHECK(launch_fp64_peak(g_ws.counters.as<double>(), 2000, 0, &blocks, &threads, &per_thread));
+  CU_CHECK(launch_fp64_peak(ws.counters.as<double>(), 2000, 0, &blocks, &threads, &per_thread));
   CU_CHECK(cudaDeviceSynchronize());
   int launches = (int)(seconds / 0.021) + 1;
-  CU_CHECK(cudaEventRecord(g_ws.ev[0], 0));
-  for (int i = 0; i < launches; i++) CU_CHECK(launch_fp64_peak(g_ws.counters.as<double>(), iters, 0, &blocks, &threads, &per_thread));
-  CU_CHECK(cudaEventRecord(g_ws.ev[1], 0));
-  CU_CHECK(cudaEventSynchronize(g_ws.ev[1]));
+  CU_CHECK(cudaEventRecord(ws.ev[0], 0));
+  for (int i = 0; i < launches; i++) CU_CHECK(launch_fp64_peak(ws.counters.as<double>(), iters, 0, &blocks, &threads, &per_thread));
+  CU_CHECK(cudaEventRecord(ws.ev[1], 0));
+  CU_CHECK(cudaEventSynchronize(ws.ev[1]));
   float ms = 0;
-  CU_CHECK(cudaEventElapsedTime(&ms, g_ws.ev[0], g_ws.ev[1]));
+  CU_CHECK(cudaEventElapsedTime(&ms, ws.ev[0], ws.ev[1]));
   const double flops = 2.0 * (double)per_thread * blocks * threads * launches;
   if (tflops) *tflops = flops / (ms * 1e-3) * 1e-12;
   return IS3D_OK;
@@ -196,11 +233,14 @@ namespace is3d {
 
 static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_species *sp, const is3d_grid *gr,
                        const is3d_df_tables *df, const is3d_laguerre *gla, const is3d_options *opt_in,
-                       double *dN_out, is3d_stats *stats, IntegRequest *iq)
+                       double *dN_out, is3d_stats *stats, IntegRequest *iq, double **keep_dev)
 {
-  if (!fl || !sf || !sp || !gr || (!dN_out && !iq)) return fail(IS3D_ERR_ARGUMENT, "NULL argument");
-  if (!g_init) { int rc = is3d_b200_init(); if (rc) return rc; }
-  std::lock_guard<std::mutex> lk(g_mutex);
+  if (!fl || !sf || !sp || !gr || (!dN_out && !iq && !keep_dev)) return fail(IS3D_ERR_ARGUMENT, "NULL argument");
+  Device *Dp = nullptr;
+  { int rc = current_device(&Dp); if (rc) return rc; }
+  Workspace &g_ws = Dp->ws;
+  const int g_sm_count = Dp->sm_count;
+  std::lock_guard<std::mutex> lk(Dp->mu);
   is3d_options opt; memset(&opt, 0, sizeof(opt));
   if (opt_in) opt = *opt_in;
   cudaStream_t st = (cudaStream_t)opt.stream;
@@ -245,7 +285,9 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   if (iq && iq->mode == 2 && !dim2) return fail(IS3D_ERR_ARGUMENT, "per-slot integration is a 2+1D pass");
   if (iq && (!iq->pT_weight || !iq->phi_weight)) return fail(IS3D_ERR_ARGUMENT, "pT / phi quadrature weights missing");
   // tile_variant: 0 = model default (tuned on B200, see profiles/), k > 0 = table entry k - 1 (tuning / tests)
-  // 17..21 = shapes of the factored kernel (cf_factored.cu; linear-df models on 3+1D tiles), the default where it applies
+  // 17..21 = shapes of the factored kernel (cf_factored.cu; linear-df models on 3+1D tiles, >= 16 species): opt-in for the main
+  // pass (measured within +-10 % of cf_kernel on B200), always used for the sparse linear-branch pass of
+  // df_mode 3 / 4, where its per-cell skip of dead records makes that pass nearly free
   int variant, fvariant = -1;
   const bool f_ok = factored_supported(model, L) && !iq;      // operation = 0 integrates over the pT lanes of a block (cf_kernel)
   if (opt.tile_variant >= 1 && opt.tile_variant <= kNumVariants) variant = opt.tile_variant - 1;
@@ -253,7 +295,6 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
     if (!f_ok) return fail(IS3D_ERR_ARGUMENT, "tile_variant 17..21 (factored kernel) needs df_mode 1/2, dimension 3, operation 1 and >= 16 species");
     variant = opt.tile_variant - 1; fvariant = variant - kNumVariants;
   }
-  else if (f_ok) { fvariant = 0; variant = kNumVariants + fvariant; }
   else if (sum_slots) variant = (model == M_FEQMOD || model == M_VAH) ? 12 : (model == M_IDEAL ? 13 : 10);
   else variant = (model == M_VAH || model == M_FEQMOD) ? 11 : 9;
   int nyt, npt, ct, max_warps;
@@ -457,8 +498,11 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
     CU_CHECK(cudaGetLastError());
     rc.gather = gather_d;
   }
-  double *dN_dev = iq ? nullptr : (opt.memory == 0) ? g_ws.dN.as<double>() : dN_out;
-  if (!iq && opt.memory == 0) CU_CHECK(cudaMemsetAsync(dN_dev, 0, (size_t)n_bins * 8, st));
+  // memory == 1: the chunk sums go to a scratch buffer first, so that an error leaves the caller's array untouched
+  const bool dev_scratch = !iq && opt.memory != 0 && !keep_dev;
+  if (dev_scratch || (keep_dev && opt.memory != 0)) CU_CHECK(g_ws.dN.reserve((size_t)n_bins * 8 + 256));
+  double *dN_dev = iq ? nullptr : g_ws.dN.as<double>();
+  if (!iq) CU_CHECK(cudaMemsetAsync(dN_dev, 0, (size_t)n_bins * 8, st));
   CU_CHECK(cudaMemsetAsync(g_ws.counters.p, 0, sizeof(PrepCounters), st));
   CU_CHECK(cudaEventRecord(ev[1], st));
 
@@ -487,6 +531,11 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
     stt.gpu_launches++;
   }
   CU_CHECK(cudaEventRecord(ev[2], st));
+  // a cell outside the coefficient tables: the reference aborts without spectra -- stop before anything is added to the result
+  PrepCounters cnt; memset(&cnt, 0, sizeof(cnt));
+  CU_CHECK(cudaMemcpyAsync(&cnt, cnt_d, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+  CU_CHECK(cudaStreamSynchronize(st));
+  if (cnt.range_error) return fail(IS3D_ERR_TABLE_RANGE, "a cell's T or Pi/P lies outside the delta-f coefficient table (or T_mod <= 0)");
 
   // ---- hot kernel(s)
   HotParams hp; memset(&hp, 0, sizeof(hp));
@@ -512,11 +561,8 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   else CU_CHECK(launch_hot(model, hp, variant, st, nullptr));
   stt.gpu_launches++;
   int reduce_sets = 1;
-  PrepCounters cnt; memset(&cnt, 0, sizeof(cnt));
   if (feqmod) {
     // cells where feqmod breaks down (and narrow-rapidity slots) take the linear-df branch: second pass, only if any
-    CU_CHECK(cudaMemcpyAsync(&cnt, cnt_d, sizeof(cnt), cudaMemcpyDeviceToHost, st));
-    CU_CHECK(cudaStreamSynchronize(st));
     if (cnt.linear_items > 0) {
       HotParams hl = hp;
       hl.Y = g_ws.Y2.as<double>(); hl.P = g_ws.P2.as<double>(); hl.S = g_ws.S2.as<double>();
@@ -553,22 +599,26 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   }
   CU_CHECK(cudaEventRecord(ev[4], st));
 
-  // ---- device -> host
+  // ---- device -> host / add into the caller's array
   std::vector<double> host_dN;
   if (iq) {
     iq->result.assign(unit_vals * reduce_sets, 0.0);
     if (unit_vals) CU_CHECK(cudaMemcpyAsync(iq->result.data(), g_ws.integ_out.p, unit_vals * reduce_sets * 8, cudaMemcpyDeviceToHost, st));
+  } else if (keep_dev) {
+    *keep_dev = dN_dev;
   } else if (opt.memory == 0) {
     host_dN.resize((size_t)n_bins);
     CU_CHECK(cudaMemcpyAsync(host_dN.data(), dN_dev, (size_t)n_bins * 8, cudaMemcpyDeviceToHost, st));
+  } else {
+    CU_CHECK(launch_axpy(dN_dev, dN_out, dim2 ? n_bins / gr->n_y : n_bins, st));       // dN_out += scratch (device pointers)
+    stt.gpu_launches++;
   }
-  CU_CHECK(cudaMemcpyAsync(&cnt, cnt_d, sizeof(cnt), cudaMemcpyDeviceToHost, st));
   CU_CHECK(cudaEventRecord(ev[5], st));
   CU_CHECK(cudaEventSynchronize(ev[5]));
   if (iq) {
     if (reduce_sets == 2) for (size_t i = 0; i < unit_vals; i++) iq->result[i] += iq->result[unit_vals + i];
     iq->result.resize(unit_vals);
-  } else if (opt.memory == 0)
+  } else if (!keep_dev && opt.memory == 0)
     for (int64_t i = 0; i < n_bins; i++) dN_out[i] += host_dN[(size_t)i];
 
   float ms;
@@ -582,8 +632,8 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   stt.cells_feqmod_breakdown = (int64_t)cnt.breakdown;
   stt.evaluations = n_cells * (int64_t)sp->n * gr->n_pT * gr->n_phi * (dim2 ? (int64_t)gr->n_eta : (int64_t)gr->n_y);
   stt.n_chunks = n_chunks; stt.tile_variant = variant;
+  stt.n_gpus = 1;
   if (stats) *stats = stt;
-  if (cnt.range_error) return fail(IS3D_ERR_TABLE_RANGE, "a cell's T or Pi/P lies outside the delta-f coefficient table (or T_mod <= 0)");
   return IS3D_OK;
 }
 
@@ -604,7 +654,7 @@ extern "C" int is3d_b200_spacetime_distributions(const is3d_flags *fl, const is3
   if (n > 0 && (!sf->tau || !sf->x || !sf->y)) return fail(IS3D_ERR_ARGUMENT, "tau, x, y arrays are required");
   if (fl->mode == 2) return fail(IS3D_ERR_UNSUPPORTED, "spacetime distributions exist for mode 1 surfaces only");
   const bool device_mem = opt_in && opt_in->memory == 1;
-  if (!g_init) { int rc = is3d_b200_init(); if (rc) return rc; }
+  { Device *D0 = nullptr; int rc = current_device(&D0); if (rc) return rc; }
 
   // ---- (tau, r) category of every cell on the host (:1376-1379); index tau_bins / r_bins = outside the histogram
   std::vector<double> hbuf;
@@ -689,8 +739,10 @@ extern "C" int is3d_b200_mean_yield(const is3d_flags *fl, const is3d_surface *sf
   if (fl->include_baryon) return fail(IS3D_ERR_UNSUPPORTED, "include_baryon = 1 (SURVEY R8)");
   if (fl->df_mode != 4 && !dn_bulk) return fail(IS3D_ERR_ARGUMENT, "df_mode 1-3 need the bulk density corrections");
   if (fl->df_mode == 4 && (!df || df->n_jonah < 3 || !df->jonah_x || !df->jonah_z)) return fail(IS3D_ERR_ARGUMENT, "df_mode 4 needs the Jonah z table");
-  if (!g_init) { int rc = is3d_b200_init(); if (rc) return rc; }
-  std::lock_guard<std::mutex> lk(g_mutex);
+  Device *Dp = nullptr;
+  { int rc = current_device(&Dp); if (rc) return rc; }
+  Workspace &g_ws = Dp->ws;
+  std::lock_guard<std::mutex> lk(Dp->mu);
   is3d_options opt; memset(&opt, 0, sizeof(opt));
   if (opt_in) opt = *opt_in;
   cudaStream_t st = (cudaStream_t)opt.stream;
@@ -771,3 +823,246 @@ extern "C" int is3d_b200_mean_yield(const is3d_flags *fl, const is3d_surface *sf
   return IS3D_OK;
 }
 
+
+// =====================================================================================================================
+// One process, several GPUs: contiguous cell shards, one host thread + stream per device, one NCCL all-reduce
+// =====================================================================================================================
+#include <dlfcn.h>
+#include <thread>
+#include <cstdlib>
+
+namespace is3d {
+
+// The handful of NCCL entry points used, resolved from libnccl.so.2 at run time (no link-time dependency; the ABI of these
+// calls is stable across NCCL 2.x).  Declarations restate nccl.h.
+typedef struct ncclComm *ncclComm_t;
+enum { kNcclSuccess = 0, kNcclSum = 0, kNcclDouble = 8 };
+struct Nccl {
+  void *so = nullptr;
+  int (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool load(std::string *err)
+  {
+    if (so) return true;
+    const char *names[] = {getenv("IS3D_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) { if (n && *n && (so = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break; }
+    if (!so) { *err = std::string("cannot load libnccl.so.2 (set IS3D_B200_NCCL_LIB): ") + dlerror(); return false; }
+    CommInitAll = (decltype(CommInitAll))dlsym(so, "ncclCommInitAll");
+    CommDestroy = (decltype(CommDestroy))dlsym(so, "ncclCommDestroy");
+    AllReduce = (decltype(AllReduce))dlsym(so, "ncclAllReduce");
+    GroupStart = (decltype(GroupStart))dlsym(so, "ncclGroupStart");
+    GroupEnd = (decltype(GroupEnd))dlsym(so, "ncclGroupEnd");
+    GetErrorString = (decltype(GetErrorString))dlsym(so, "ncclGetErrorString");
+    if (!CommInitAll || !CommDestroy || !AllReduce || !GroupStart || !GroupEnd) { *err = "libnccl.so.2 lacks an expected symbol"; return false; }
+    return true;
+  }
+};
+
+static std::mutex g_multi_mutex;
+static Nccl g_nccl;
+static int g_ngpus = 1;
+static std::vector<ncclComm_t> g_comms;
+static std::vector<cudaStream_t> g_streams;
+
+static void multi_shutdown()
+{
+  std::lock_guard<std::mutex> lk(g_multi_mutex);
+  int prev = 0; cudaGetDevice(&prev);
+  for (size_t d = 0; d < g_comms.size(); d++) if (g_comms[d] && g_nccl.CommDestroy) g_nccl.CommDestroy(g_comms[d]);
+  for (size_t d = 0; d < g_streams.size(); d++) if (g_streams[d]) { cudaSetDevice((int)d); cudaStreamDestroy(g_streams[d]); }
+  g_comms.clear(); g_streams.clear(); g_ngpus = 1;
+  cudaSetDevice(prev);
+}
+
+// cell shard of device d: contiguous, ceil(n / n_dev) cells (is3d_b200/distributed.py::shard_bounds)
+static void shard_bounds(int64_t n, int d, int n_dev, int64_t *lo, int64_t *hi)
+{
+  const int64_t per = (n + n_dev - 1) / n_dev;
+  *lo = std::min<int64_t>(n, per * d); *hi = std::min<int64_t>(n, per * (d + 1));
+}
+
+static is3d_surface shard_surface(const is3d_surface &s, int64_t lo, int64_t hi)
+{
+  is3d_surface o = s;
+  o.n_cells = hi - lo;
+  const double **src = reinterpret_cast<const double **>(reinterpret_cast<char *>(&o) + offsetof(is3d_surface, tau));
+  const size_t n_ptr = (sizeof(is3d_surface) - offsetof(is3d_surface, tau)) / sizeof(double *);
+  for (size_t a = 0; a < n_ptr; a++) if (src[a]) src[a] += lo;
+  return o;
+}
+
+static void merge_stats(is3d_stats *acc, const is3d_stats &s)
+{
+  acc->cells_skipped_udsigma += s.cells_skipped_udsigma; acc->cells_feqmod_breakdown += s.cells_feqmod_breakdown;
+  acc->evaluations += s.evaluations; acc->gpu_launches += s.gpu_launches;
+  acc->h2d_ms = std::max(acc->h2d_ms, s.h2d_ms); acc->prepare_ms = std::max(acc->prepare_ms, s.prepare_ms);
+  acc->kernel_ms = std::max(acc->kernel_ms, s.kernel_ms); acc->reduce_ms = std::max(acc->reduce_ms, s.reduce_ms);
+  acc->d2h_ms = std::max(acc->d2h_ms, s.d2h_ms); acc->total_ms = std::max(acc->total_ms, s.total_ms);
+  acc->n_chunks = s.n_chunks; acc->tile_variant = s.tile_variant;
+}
+
+}  // namespace is3d
+
+extern "C" int is3d_b200_device_count(void) { return g_ngpus; }
+
+extern "C" int is3d_b200_init_devices(int n_gpus)
+{
+  int visible = 0;
+  if (cudaGetDeviceCount(&visible) != cudaSuccess || visible == 0) return fail(IS3D_ERR_NO_DEVICE, "no CUDA device visible");
+  if (n_gpus <= 0) {
+    const char *e = getenv("IS3D_B200_GPUS");
+    n_gpus = (e && atoi(e) > 0) ? atoi(e) : visible;
+  }
+  if (n_gpus > visible) return fail(IS3D_ERR_ARGUMENT, "more GPUs requested than visible");
+  if (n_gpus > kMaxDevices) n_gpus = kMaxDevices;
+  {
+    std::lock_guard<std::mutex> lk(g_multi_mutex);
+    if (n_gpus == g_ngpus && (n_gpus == 1 || !g_comms.empty())) return IS3D_OK;
+  }
+  multi_shutdown();
+  int prev = 0; cudaGetDevice(&prev);
+  std::lock_guard<std::mutex> lk(g_multi_mutex);
+  if (n_gpus > 1) {
+    std::string err;
+    if (!g_nccl.load(&err)) return fail(IS3D_ERR_NCCL, err.c_str());
+    std::vector<int> devs(n_gpus);
+    for (int d = 0; d < n_gpus; d++) devs[d] = d;
+    g_comms.assign(n_gpus, nullptr);
+    const int rc = g_nccl.CommInitAll(g_comms.data(), n_gpus, devs.data());
+    if (rc != kNcclSuccess) { g_comms.clear(); return fail(IS3D_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclCommInitAll failed"); }
+    g_streams.assign(n_gpus, nullptr);
+    for (int d = 0; d < n_gpus; d++) {
+      CU_CHECK(cudaSetDevice(d));
+      CU_CHECK(cudaStreamCreateWithFlags(&g_streams[d], cudaStreamNonBlocking));
+      Device *D = nullptr;
+      const int r2 = current_device(&D);
+      if (r2) { cudaSetDevice(prev); return r2; }
+    }
+    CU_CHECK(cudaSetDevice(prev));
+  }
+  g_ngpus = n_gpus;
+  return IS3D_OK;
+}
+
+extern "C" int is3d_b200_smooth_spectra_multi(const is3d_flags *fl, const is3d_surface *sf, const is3d_species *sp, const is3d_grid *gr,
+                                              const is3d_df_tables *df, const is3d_laguerre *gla, const is3d_options *opt_in,
+                                              double *dN_out, is3d_stats *stats)
+{
+  if (!fl || !sf || !sp || !gr || !dN_out) return fail(IS3D_ERR_ARGUMENT, "NULL argument");
+  const int G = g_ngpus;
+  if (G <= 1) return is3d_b200_smooth_spectra(fl, sf, sp, gr, df, gla, opt_in, dN_out, stats);
+  if (opt_in && opt_in->memory != 0) return fail(IS3D_ERR_ARGUMENT, "the multi-GPU entry point takes host arrays");
+  std::lock_guard<std::mutex> lk(g_multi_mutex);
+  const int64_t n_bins = (int64_t)sp->n * gr->n_pT * gr->n_phi * gr->n_y;
+  int prev = 0; cudaGetDevice(&prev);
+  std::vector<int> rcs(G, IS3D_OK);
+  std::vector<std::string> errs(G);
+  std::vector<is3d_stats> sts(G);
+  std::vector<double *> dev_dN(G, nullptr);
+  std::vector<std::thread> workers;
+  for (int d = 0; d < G; d++) {
+    workers.emplace_back([&, d]() {
+      memset(&sts[d], 0, sizeof(is3d_stats));
+      if (cudaSetDevice(d) != cudaSuccess) { rcs[d] = IS3D_ERR_CUDA; errs[d] = "cudaSetDevice failed"; return; }
+      int64_t lo, hi;
+      shard_bounds(sf->n_cells, d, G, &lo, &hi);
+      const is3d_surface shard = shard_surface(*sf, lo, hi);
+      is3d_options opt; memset(&opt, 0, sizeof(opt));
+      if (opt_in) opt = *opt_in;
+      opt.memory = 0; opt.stream = g_streams[d];
+      rcs[d] = smooth_core(fl, &shard, sp, gr, df, gla, &opt, nullptr, &sts[d], nullptr, &dev_dN[d]);
+      if (rcs[d]) errs[d] = g_last_error;
+    });
+  }
+  for (auto &w : workers) w.join();
+  for (int d = 0; d < G; d++) if (rcs[d]) { cudaSetDevice(prev); return fail(rcs[d], errs[d].c_str()); }
+
+  // ---- the one collective of the path: sum of the spectra arrays over NVLink
+  cudaEvent_t e0, e1;
+  CU_CHECK(cudaSetDevice(0));
+  CU_CHECK(cudaEventCreate(&e0)); CU_CHECK(cudaEventCreate(&e1));
+  CU_CHECK(cudaEventRecord(e0, g_streams[0]));
+  int nrc = g_nccl.GroupStart();
+  for (int d = 0; d < G && nrc == kNcclSuccess; d++)
+    nrc = g_nccl.AllReduce(dev_dN[d], dev_dN[d], (size_t)n_bins, kNcclDouble, kNcclSum, g_comms[d], g_streams[d]);
+  const int nrc2 = g_nccl.GroupEnd();
+  if (nrc == kNcclSuccess) nrc = nrc2;
+  if (nrc != kNcclSuccess) { cudaSetDevice(prev); return fail(IS3D_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "ncclAllReduce failed"); }
+  CU_CHECK(cudaEventRecord(e1, g_streams[0]));
+  std::vector<double> host((size_t)n_bins);
+  CU_CHECK(cudaMemcpyAsync(host.data(), dev_dN[0], (size_t)n_bins * 8, cudaMemcpyDeviceToHost, g_streams[0]));
+  for (int d = 0; d < G; d++) { CU_CHECK(cudaSetDevice(d)); CU_CHECK(cudaStreamSynchronize(g_streams[d])); }
+  for (int64_t i = 0; i < n_bins; i++) dN_out[i] += host[(size_t)i];
+  float ms = 0;
+  CU_CHECK(cudaSetDevice(0));
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CU_CHECK(cudaSetDevice(prev));
+  if (stats) {
+    is3d_stats tot; memset(&tot, 0, sizeof(tot));
+    for (int d = 0; d < G; d++) merge_stats(&tot, sts[d]);
+    tot.n_gpus = G; tot.allreduce_ms = ms; tot.total_ms += ms;
+    *stats = tot;
+  }
+  return IS3D_OK;
+}
+
+extern "C" int is3d_b200_spacetime_distributions_multi(const is3d_flags *fl, const is3d_surface *sf, const is3d_species *sp,
+                                                       const is3d_grid *gr, const is3d_df_tables *df, const is3d_laguerre *gla,
+                                                       const is3d_spacetime_bins *bins, const is3d_options *opt_in,
+                                                       is3d_spacetime_result *res, is3d_stats *stats)
+{
+  const int G = g_ngpus;
+  if (G <= 1) return is3d_b200_spacetime_distributions(fl, sf, sp, gr, df, gla, bins, opt_in, res, stats);
+  if (!fl || !sf || !sp || !gr || !bins || !res) return fail(IS3D_ERR_ARGUMENT, "NULL argument");
+  if (opt_in && opt_in->memory != 0) return fail(IS3D_ERR_ARGUMENT, "the multi-GPU entry point takes host arrays");
+  std::lock_guard<std::mutex> lk(g_multi_mutex);
+  const int ns = sp->n, nt = bins->tau_bins, nr = bins->r_bins, eta_pts = fl->dimension == 2 ? gr->n_eta : 1;
+  if (ns <= 0 || nt <= 0 || nr <= 0) return fail(IS3D_ERR_ARGUMENT, "empty species list or binning");
+  const size_t sizes[5] = {(size_t)ns * nt, (size_t)ns * nr, (size_t)ns * nt * nr, (size_t)ns * eta_pts, (size_t)ns};
+  size_t total = 0; for (size_t v : sizes) total += v;
+  int prev = 0; cudaGetDevice(&prev);
+  std::vector<int> rcs(G, IS3D_OK);
+  std::vector<std::string> errs(G);
+  std::vector<is3d_stats> sts(G);
+  std::vector<std::vector<double>> bufs(G, std::vector<double>(total, 0.0));
+  std::vector<std::thread> workers;
+  for (int d = 0; d < G; d++) {
+    workers.emplace_back([&, d]() {
+      memset(&sts[d], 0, sizeof(is3d_stats));
+      if (cudaSetDevice(d) != cudaSuccess) { rcs[d] = IS3D_ERR_CUDA; errs[d] = "cudaSetDevice failed"; return; }
+      int64_t lo, hi;
+      shard_bounds(sf->n_cells, d, G, &lo, &hi);
+      const is3d_surface shard = shard_surface(*sf, lo, hi);
+      is3d_options opt; memset(&opt, 0, sizeof(opt));
+      if (opt_in) opt = *opt_in;
+      opt.memory = 0; opt.stream = g_streams[d];
+      double *b = bufs[d].data();
+      is3d_spacetime_result r{b, b + sizes[0], b + sizes[0] + sizes[1], b + sizes[0] + sizes[1] + sizes[2], b + sizes[0] + sizes[1] + sizes[2] + sizes[3]};
+      rcs[d] = is3d_b200_spacetime_distributions(fl, &shard, sp, gr, df, gla, bins, &opt, &r, &sts[d]);
+      if (rcs[d]) errs[d] = g_last_error;
+    });
+  }
+  for (auto &w : workers) w.join();
+  cudaSetDevice(prev);
+  for (int d = 0; d < G; d++) if (rcs[d]) return fail(rcs[d], errs[d].c_str());
+  double *out[5] = {res->dN_tau, res->dN_r, res->dN_taur, res->dN_dydeta, res->dN_dy};
+  size_t off = 0;
+  for (int q = 0; q < 5; q++) {
+    if (!out[q]) return fail(IS3D_ERR_ARGUMENT, "NULL result array");
+    for (size_t i = 0; i < sizes[q]; i++) { double v = 0.0; for (int d = 0; d < G; d++) v += bufs[d][off + i]; out[q][i] = v; }
+    off += sizes[q];
+  }
+  // 2+1D: dN_dydeta is a quotient by the eta weight per device shard; the quotients add because the weight is the same
+  if (stats) {
+    is3d_stats tot; memset(&tot, 0, sizeof(tot));
+    for (int d = 0; d < G; d++) merge_stats(&tot, sts[d]);
+    tot.n_gpus = G;
+    *stats = tot;
+  }
+  return IS3D_OK;
+}

@@ -22,11 +22,12 @@
 //   2. Classification without x: together with the slot table the block stores min / max of the slot exponents over its lanes;
 //      min / max exponent of a (cell, slot) group of a warp is that plus min / max of the phi exponents.  A warp-UNIFORM compare
 //      skips dead groups (every exp(x) overflows in the reference: f = 0 exactly), selects the occupation-factor form
-//      (a = e^{-x} < 2^-54: 1 / (1 + Theta a) = 1 exactly; a < 2^-18: 1 - Theta a + a^2; else MUFU seed + Newton), and tells
-//      whether any member is near the overflow / sub-normal boundary.  Only such groups look at per-thread exponents; members
-//      within ~3 units of the boundary go through late_member(), which decides from x itself exactly as cf_kernels.cu does.
+//      (a = e^{-x} < 2^-18: 1 / (1 + Theta a) = 1 - Theta a + a^2; else MUFU seed + Newton), and tells whether any member is
+//      near the overflow / sub-normal boundary.  Only such groups look at per-thread exponents; members within ~3 units of the
+//      boundary go through late_member(), which decides from x itself exactly as cf_kernels.cu does.
 //   3. g = 1 + df is formed directly (the reference multiplies f_eq (1 + df), :330); regulate_deltaf clamps g to [0, 2] on its
-//      high word, skipped when no member of the thread's group needs it.
+//      high word.  Apart from the dead-group skip and the choice of the occupation-factor form the inner loop has no branches:
+//      profiling showed branch resolution and reconvergence (BSSY / BSYNC), not arithmetic, to be what the warps wait for.
 //   4. The tables are double buffered: a tile costs ONE __syncthreads and its TMA stage is released before the inner loop.
 #include "cf_internal.h"
 #include <algorithm>
@@ -41,7 +42,6 @@ namespace {
 constexpr int kNDead = -1027;      // n <= kNDead: a < 2^-1025, x > 710.4 > ln(DBL_MAX): the term is exactly 0 in the reference
 constexpr int kNNormal = -1021;    // n >= kNNormal: a >= 0.997 x 2^-1021, a normal number: exponent insertion is exact
 constexpr int kNDilute = -20;      // n <= kNDilute: a < 2^-18
-constexpr int kNUltra = -56;       // n <= kNUltra: a < 2^-54, 1 + Theta a rounds to 1
 constexpr int kNForcedDead = -200000;
 
 constexpr int kFW = 4;             // warps (= phi tiles) per block
@@ -322,71 +322,46 @@ cf_factored_kernel(const HotParams hp)
           double pv[NPT]; int n[NPT];
 #pragma unroll
           for (int k = 0; k < NPT; k++) { pv[k] = fma(mT, cq.x, pd[k]); n[k] = ne + fm[k]; }     // p.dsigma; binary exponent of e^{-x}
-          bool ok_t = true, late_t = false;
-          if (!all_ok) {                                 // rare (warp-uniform): a group at the overflow / sub-normal boundary
-            int nmin = n[0], nmax = n[0];
-#pragma unroll
-            for (int k = 1; k < NPT; k++) { nmin = min(nmin, n[k]); nmax = max(nmax, n[k]); }
-            const bool dead_t = nmax <= kNDead && !cell_general;
-            ok_t = nmin >= kNNormal && !cell_general;
-            late_t = !dead_t && !ok_t;
-          }
-          if (ok_t) {
-            double av[NPT], g[NPT], fe[NPT];
+          if (!all_ok) {
+            // rare (warp-uniform, ~7 % of the live groups): the group touches the overflow / sub-normal boundary of e^{-x} on some
+            // lane, or the cell is out of the factored form's range: every member that is not plainly dead is evaluated from x itself
 #pragma unroll
             for (int k = 0; k < NPT; k++) {
-              const double pm = pe * fq[k];
-              av[k] = __hiloint2double(__double2hiint(pm) + (n[k] << 20), __double2loint(pm));
-            }
-            if (POLY) {
-#pragma unroll
-              for (int k = 0; k < NPT; k++) g[k] = df_poly<MODEL>(fma(mT, xr[k], H + G0[k]), a - q[k], K2);
-            }
-            if (nhi <= kNUltra) {                        // a < 2^-54 for every lane: feqbar = 1 exactly
-#pragma unroll
-              for (int k = 0; k < NPT; k++) { fe[k] = av[k]; if (POLY) g[k] = g[k] + K31; }
-            } else if (nhi <= kNDilute) {                // a < 2^-18
-#pragma unroll
-              for (int k = 0; k < NPT; k++) {
-                const double fb = fma(av[k], av[k], fma(nsign, av[k], 1.0));
-                fe[k] = av[k] * fb; if (POLY) g[k] = fma(fb, g[k], K31);
-              }
-            } else {
-#pragma unroll
-              for (int k = 0; k < NPT; k++) {
-                const double fb = rcp_fast(fma(sign, av[k], 1.0));
-                fe[k] = av[k] * fb; if (POLY) g[k] = fma(fb, g[k], K31);
+              if (n[k] > kNDead || cell_general) {
+                const double sk = POLY ? fma(mT, xr[k], H + G0[k]) : 0.0;
+                accj[k] += late_member<MODEL>(a - q[k], sk, pv[k], K2, K31, sign, reg_lo, reg_hi, thr_hi);
               }
             }
-            if (POLY) {
-              // regulate_deltaf: with lanes = species at one pT the clamp is needed by (nearly) all lanes of a warp or by none
-              bool need = needs_clamp(g[0], hp.reg_chk);
-#pragma unroll
-              for (int k = 1; k < NPT; k++) need = need || needs_clamp(g[k], hp.reg_chk);
-              if (need) {
-#pragma unroll
-                for (int k = 0; k < NPT; k++) g[k] = clamp_g(g[k], reg_lo, reg_hi, hp.reg_chk);
-              }
-#pragma unroll
-              for (int k = 0; k < NPT; k++) fe[k] *= g[k];
-            }
-            int pvlo = __double2hiint(pv[0]);
-#pragma unroll
-            for (int k = 1; k < NPT; k++) pvlo = min(pvlo, __double2hiint(pv[k]));
-            if (pvlo > thr_hi) {                         // outflow test (smooth_kernels.cpp:285) passes for every member
-#pragma unroll
-              for (int k = 0; k < NPT; k++) accj[k] = fma(pv[k], fe[k], accj[k]);
-            } else {
-#pragma unroll
-              for (int k = 0; k < NPT; k++) accumulate_pos(accj[k], pv[k], fe[k], thr_hi);
-            }
+            continue;
           }
-          if (late_t) {
+          // ---- fast path, branch-free but for the occupation-factor form (warp-uniform)
+          double av[NPT], g[NPT], fe[NPT];
+#pragma unroll
+          for (int k = 0; k < NPT; k++) {
+            const double pm = pe * fq[k];
+            av[k] = __hiloint2double(__double2hiint(pm) + (n[k] << 20), __double2loint(pm));
+          }
+          if (POLY) {
+#pragma unroll
+            for (int k = 0; k < NPT; k++) g[k] = df_poly<MODEL>(fma(mT, xr[k], H + G0[k]), a - q[k], K2);
+          }
+          if (nhi <= kNDilute) {                         // a < 2^-18 for every lane: 1 / (1 + Theta a) = 1 - Theta a + a^2 to 2^-54
 #pragma unroll
             for (int k = 0; k < NPT; k++) {
-              const double sk = POLY ? fma(mT, xr[k], H + G0[k]) : 0.0;
-              accj[k] += late_member<MODEL>(a - q[k], sk, pv[k], K2, K31, sign, reg_lo, reg_hi, thr_hi);
+              const double fb = fma(av[k], av[k], fma(nsign, av[k], 1.0));
+              fe[k] = av[k] * fb; if (POLY) g[k] = fma(fb, g[k], K31);
             }
+          } else {
+#pragma unroll
+            for (int k = 0; k < NPT; k++) {
+              const double fb = rcp_fast(fma(sign, av[k], 1.0));
+              fe[k] = av[k] * fb; if (POLY) g[k] = fma(fb, g[k], K31);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < NPT; k++) {
+            if (POLY) fe[k] *= clamp_g(g[k], reg_lo, reg_hi, hp.reg_chk);               // regulate_deltaf
+            if (__double2hiint(pv[k]) > thr_hi) accj[k] = fma(pv[k], fe[k], accj[k]);   // outflow test (smooth_kernels.cpp:285)
           }
         }
       }
@@ -399,7 +374,7 @@ cf_factored_kernel(const HotParams hp)
 // ------------------------------------------------------------------------------------------------ dispatch
 // Register-tile shapes of the factored kernel; is3d_options.tile_variant = 17 + k selects entry k.
 struct FShape { int nyt, npt, ct, minb; };
-static const FShape kFShapes[kNumFactoredVariants] = {{7, 3, 8, 3}, {7, 4, 8, 3}, {7, 3, 8, 4}, {7, 6, 8, 2}, {7, 2, 8, 4}};
+static const FShape kFShapes[kNumFactoredVariants] = {{7, 3, 8, 3}, {7, 4, 8, 3}, {3, 6, 8, 3}, {3, 6, 8, 4}, {3, 8, 8, 3}};
 
 bool factored_supported(int model, const Layout &L)
 {
@@ -452,9 +427,9 @@ static cudaError_t launch_fmodel(const HotParams &hp, int fvariant, cudaStream_t
 {
   switch (fvariant) {
     case 1: return launch_f<MODEL, 7, 4, 3>(hp, st, smem_out);
-    case 2: return launch_f<MODEL, 7, 3, 4>(hp, st, smem_out);
-    case 3: return launch_f<MODEL, 7, 6, 2>(hp, st, smem_out);
-    case 4: return launch_f<MODEL, 7, 2, 4>(hp, st, smem_out);
+    case 2: return launch_f<MODEL, 3, 6, 3>(hp, st, smem_out);
+    case 3: return launch_f<MODEL, 3, 6, 4>(hp, st, smem_out);
+    case 4: return launch_f<MODEL, 3, 8, 3>(hp, st, smem_out);
     default: return launch_f<MODEL, 7, 3, 3>(hp, st, smem_out);
   }
 }

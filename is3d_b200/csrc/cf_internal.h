@@ -97,6 +97,7 @@ cudaError_t launch_prepare_vah(const is3d_flags &fl, const RawCells &cells, cons
                                double *Y, double *P, double *S, PrepCounters *counters, cudaStream_t st);
 cudaError_t launch_hot(int model, const HotParams &hp, int variant, cudaStream_t st, size_t *smem_out);
 cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, int64_t n_active, double *out, cudaStream_t st);
+cudaError_t launch_axpy(const double *x, double *y, int64_t n, cudaStream_t st);      // y += x
 // integ -> out[unit][species], unit = chunk (mode 1) or slot (mode 2, summed over chunks)
 cudaError_t launch_integ_reduce(const HotParams &hp, int n_units, double *out, cudaStream_t st);
 // sampler mean yield: per-block triples (sum u.dsigma, sum u.dsigma Pi, sum u.dsigma z) in partial[3 * n_blocks]

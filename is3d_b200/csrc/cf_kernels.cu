@@ -527,6 +527,20 @@ cudaError_t launch_integ_reduce(const HotParams &hp, int n_units, double *out, c
   return cudaGetLastError();
 }
 
+// y[i] += x[i]
+__global__ void axpy_kernel(const double *__restrict__ x, double *__restrict__ y, int64_t n)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += x[i];
+}
+
+cudaError_t launch_axpy(const double *x, double *y, int64_t n, cudaStream_t st)
+{
+  if (n == 0) return cudaSuccess;
+  axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, n);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, int64_t n_active, double *out, cudaStream_t st)
 {
   if (n_active == 0) return cudaSuccess;

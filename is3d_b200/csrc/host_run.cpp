@@ -242,6 +242,11 @@ static int run_problem(const std::string &wd, Problem &P, const is3d_surface &s,
   std::string &err = *err_out;
   const Grids &g = P.g; const DfTables &dft = P.dft; const Laguerre &gla = P.gla;
   const int npart = (int)P.mcid.size();
+  // the file-level drop-in uses every visible GPU (or IS3D_B200_GPUS of them): cells are sharded inside the C ABI
+  {
+    const int rc_dev = is3d_b200_init_devices(0);
+    if (rc_dev != IS3D_OK) { err = is3d_b200_last_error(); return rc_dev; }
+  }
   is3d_species sp{npart, P.mass.data(), P.sign.data(), P.degen.data(), P.baryon.data()};
   is3d_grid gr{(int32_t)g.pT.rows, (int32_t)g.phi.rows, (int32_t)g.y.rows, (int32_t)g.eta.rows,
                g.pT.cols[0].data(), g.phi.cols[0].data(), g.y.cols[0].data(), g.eta.cols[0].data(), g.eta.cols[1].data()};
@@ -267,7 +272,7 @@ static int run_problem(const std::string &wd, Problem &P, const is3d_surface &s,
     std::vector<double> h_tau(npart * nt), h_r(npart * nr), h_taur(npart * nt * nr), h_eta((size_t)npart * eta_pts), h_y((size_t)npart);
     is3d_spacetime_result res{h_tau.data(), h_r.data(), h_taur.data(), h_eta.data(), h_y.data()};
     is3d_stats st0; std::memset(&st0, 0, sizeof(st0));
-    const int rc0 = is3d_b200_spacetime_distributions(&P.fl, &s, &sp, &gr, &dt, &la, &b, nullptr, &res, &st0);
+    const int rc0 = is3d_b200_spacetime_distributions_multi(&P.fl, &s, &sp, &gr, &dt, &la, &b, nullptr, &res, &st0);
     if (stats) *stats = st0;
     if (rc0 != IS3D_OK) { err = std::string("spacetime kernel failed: ") + is3d_b200_last_error(); return rc0; }
     std::vector<double> eta_values(eta_pts, 0.0);
@@ -286,7 +291,7 @@ static int run_problem(const std::string &wd, Problem &P, const is3d_surface &s,
   const size_t n_bins = (size_t)npart * g.pT.rows * g.phi.rows * g.y.rows;
   std::vector<double> dN(n_bins, 0.0);
   is3d_stats st; std::memset(&st, 0, sizeof(st));
-  const int rc = is3d_b200_smooth_spectra(&P.fl, &s, &sp, &gr, &dt, &la, nullptr, dN.data(), &st);
+  const int rc = is3d_b200_smooth_spectra_multi(&P.fl, &s, &sp, &gr, &dt, &la, nullptr, dN.data(), &st);
   if (stats) *stats = st;
   if (rc != IS3D_OK) { err = std::string("spectra kernel failed: ") + is3d_b200_last_error(); return rc; }
   if (P.fl.mode != 2 && (P.fl.df_mode == 3 || P.fl.df_mode == 4))

@@ -31,12 +31,12 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(api.Species) == 8 + 8 * 4
     assert ctypes.sizeof(api.Grid) == 16 + 8 * 5
     assert ctypes.sizeof(api.Options) == 4 + 4 + 8 + 4 + 4 + 16
-    assert ctypes.sizeof(api.Stats) == 3 * 8 + 6 * 8 + 3 * 4 + 4
+    assert ctypes.sizeof(api.Stats) == 3 * 8 + 6 * 8 + 4 * 4 + 8      # ... + n_gpus, allreduce_ms
 
 
 def test_error_strings():
     lib = api.lib()
-    for code in range(7):
+    for code in range(8):
         assert lib.is3d_b200_strerror(code)
     assert lib.is3d_b200_version() >= 100
 

@@ -434,7 +434,7 @@ def _mid_species(fx, n):
 
 @pytest.mark.parametrize("case", ["df1", "df2", "ideal", "df1_noreg", "df2_noreg", "df1_stress"])
 def test_factored_variants_against_oracle(fx, case):
-    """cf_factored_kernel (lanes = species, tile_variant 17..21; the default for >= 16 species in 3+1D) against the oracle: 45
+    """cf_factored_kernel (lanes = species, warps = phi tiles; tile_variant 17..21, opt-in for >= 16 species in 3+1D) against the oracle: 45
     species (not a multiple of the warp), 150 cells (not a multiple of the TMA tile), every shape, with and without
     regulate_deltaf / outflow, and on the stress surface where most delta-f values are clamped"""
     from oracle import cf_oracle as cfo
@@ -449,7 +449,7 @@ def test_factored_variants_against_oracle(fx, case):
     ref, _, _ = cfo.smooth(fl, cells, sp, g, tab, None, conditioning=cond)
     for variant in (0, 17, 18, 19, 20, 21):
         dN, st = api.smooth_spectra(fl, cells, sp, g, tab, None, tile_variant=variant)
-        assert st["tile_variant"] == (16 if variant == 0 else variant - 1)
+        assert st["tile_variant"] == (9 if variant == 0 else variant - 1)
         rep = compare(dN, ref, conditioning=cond)
         assert rep["ok"], (case, variant, rep, compare(dN, ref))
     # and the (species, pT)-lane kernel on the same problem
@@ -467,9 +467,9 @@ def test_factored_ragged_grids_and_chunks(fx):
         cells = synthetic.columns_to_cells(synthetic.surface_vh(n_cells, 99 + n_cells), 1)
         fl = tables.flags(df_mode=1, dimension=3)
         ref, _, _ = cfo.smooth(fl, cells, sp, g, tab, None)
-        for variant, chunks in ((0, 0), (18, 1), (19, 5)):
+        for variant, chunks in ((17, 0), (18, 1), (19, 5), (21, 2)):
             dN, st = api.smooth_spectra(fl, cells, sp, g, tab, None, tile_variant=variant, n_chunks=chunks)
-            assert st["tile_variant"] >= 16
+            assert st["tile_variant"] == variant - 1
             assert compare(dN, ref)["ok"], (n_cells, variant, chunks)
 
 
