@@ -161,6 +161,28 @@ int is3d_b200_spacetime_distributions_multi(const is3d_flags *flags, const is3d_
                                             const is3d_spacetime_bins *bins, const is3d_options *options,
                                             is3d_spacetime_result *result, is3d_stats *stats);
 
+/* ---- resonance-decay feed-down of the smooth spectra ------------------------------------------------
+ * Replaces EmissionFunctionArray::do_resonance_decays and the routines below it (src/cpp/emissionfunction_resonance_decays.cpp:
+ * 124-2158, called from calculate_spectra, emissionfunction.cpp:1689-1698).  The particle list is the reference's particle_info
+ * array (readindata.cpp:1440-1568: anti-baryons right behind their baryon, `stable` = first channel has one product) with the
+ * decay channels flattened: channel rows dec_first[i] .. dec_first[i] + decays[i] - 1 of dec_npart / dec_br / dec_part[row * 5 + k].
+ * chosen_pdg_index is the reference's chosen_particles_sampling_table (particle-list index of every chosen species).
+ * dN [y][phi][pT][species] (host memory, or device memory with options->memory = 1) is amended in place: parents from the last
+ * chosen species down to the second, 2- and 3-body channels, daughters that are chosen species.
+ * NOTE: the reference snapshot disables its own routine with an exit(-1) at entry (:126-129, the author's note on the MTmax
+ * handling of the interpolation); this entry point implements the body behind that guard and is checked against it. */
+typedef struct {
+  int32_t n_particles;
+  const int32_t *mcid;
+  const double *mass, *width;
+  const int32_t *stable, *decays, *dec_first;
+  const int32_t *dec_npart;
+  const double *dec_br;
+  const int32_t *dec_part;
+} is3d_particle_list;
+int is3d_b200_resonance_decays(const is3d_particle_list *particles, int32_t n_chosen, const int32_t *chosen_pdg_index,
+                               const is3d_grid *grid, int32_t dimension, const is3d_options *options, double *dN, is3d_stats *stats);
+
 /* FP64 FMA peak of the current device measured with a dependency-free DFMA chain (the roofline denominator;
  * MEASURED_PEAKS.json carries no FP64 figure).  Returns TFLOP/s in *tflops, SM clock not touched. */
 int is3d_b200_measure_fp64_peak(double *tflops, double *ms);
@@ -170,7 +192,9 @@ int is3d_b200_measure_fp64_sustained(double seconds, double *tflops);
 /* ---- host layer: the drop-in behind iS3D_parameters.dat / input/surface.dat / PDG / deltaf_coefficients / tables ----
  * Equivalent of IS3D::run_particlization(1) with operation = 1 (src/cpp/iS3D.cpp:73-191): reads the CWD-relative input
  * files under `workdir`, runs the spectra on the GPU, writes results/dN_pTdpTdphidy*.dat, results/vn_continuous/ and
- * results/dN_dy_*.dat with the reference's formats.  If dN_raw != NULL it receives the spectra (n_raw doubles max).
+ * results/dN_dy_*.dat with the reference's formats; with do_resonance_decays = 1 it then runs the feed-down and writes
+ * results/dN_pTdpTdphidy_resonance_decays.dat and results/dN_dpTdphidy_resonance_decays.dat (emissionfunction.cpp:452-488, 555-590),
+ * and dN_raw receives the amended spectra.  If dN_raw != NULL it receives the spectra (n_raw doubles max).
  * operation = 0 runs the spacetime distributions instead and writes results/spacetime_distribution/dN_taudtaudy_<mcid>.dat,
  * dN_twopirdrdy_<mcid>.dat, dN_twopitaurdtaudrdy_<mcid>.dat, dN_dydeta_<mcid>_<eta_pts>pt.dat (smooth_kernels.cpp:1112-1126,
  * 1404-1435); dN_raw then receives the raw sums concatenated as [dN_tau | dN_r | dN_taur | dN_dydeta | dN_dy]. */

@@ -392,3 +392,49 @@ def mean_yield(flags, cells, neq, dn_bulk, df_tables=None, y_cut=5.0, memory="ho
     _check(f(C.byref(fl), C.byref(sf), len(neq), m.host(neq), m.host(dn_bulk) if dn_bulk is not None else None, C.byref(dft),
              float(y_cut), C.byref(opt), C.byref(out), C.byref(st)))
     return out.value, st.as_dict()
+
+
+class ParticleList(C.Structure):
+    _I = C.POINTER(C.c_int32)
+    _fields_ = [("n_particles", C.c_int32), ("mcid", _I), ("mass", _D), ("width", _D), ("stable", _I), ("decays", _I), ("dec_first", _I),
+                ("dec_npart", _I), ("dec_br", _D), ("dec_part", _I)]
+
+
+def resonance_decays(pdg, chosen_pdg_index, grid, dimension, dN, memory="host", stream=None):
+    """Call is3d_b200_resonance_decays: feed-down of the unstable chosen species into their chosen daughters.
+
+    pdg: dict of arrays mcid, mass, width, stable, decays, dec_first, dec_npart, dec_br, dec_part[rows, 5] (tables.pdg_decay_table);
+    dN: numpy array (memory='host'; a copy is amended and returned) or float64 CUDA tensor (memory='device'; amended in place)."""
+    keep = []
+
+    def ia(x):
+        a = np.ascontiguousarray(x, dtype=np.int32); keep.append(a)
+        return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+    m = _Marshal(False)
+    p = ParticleList()
+    p.n_particles = len(pdg["mcid"])
+    p.mcid = ia(pdg["mcid"]); p.mass = m.host(pdg["mass"]); p.width = m.host(pdg["width"]); p.stable = ia(pdg["stable"])
+    p.decays = ia(pdg["decays"]); p.dec_first = ia(pdg["dec_first"]); p.dec_npart = ia(pdg["dec_npart"]); p.dec_br = m.host(pdg["dec_br"])
+    p.dec_part = ia(np.asarray(pdg["dec_part"]).ravel())
+    g = Grid()
+    g.n_pT, g.n_phi, g.n_y, g.n_eta = len(grid["pT"]), len(grid["phi"]), len(grid["y"]), len(grid["eta"])
+    for k in ("pT", "phi", "y", "eta", "eta_weight"):
+        setattr(g, k, m.host(grid[k]))
+    device = (memory == "device")
+    if device:
+        import torch
+        out = dN
+        ptr = C.c_void_p(out.data_ptr())
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+    else:
+        out = np.array(dN, dtype=np.float64, copy=True)
+        ptr = C.c_void_p(out.ctypes.data)
+    opt = Options(); opt.memory = 1 if device else 0; opt.stream = C.c_void_p(stream or 0)
+    st = Stats()
+    f = lib().is3d_b200_resonance_decays
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(ParticleList), C.c_int32, C.POINTER(C.c_int32), C.POINTER(Grid), C.c_int32, C.POINTER(Options), C.c_void_p, C.POINTER(Stats)]
+    _check(f(C.byref(p), len(chosen_pdg_index), ia(chosen_pdg_index), C.byref(g), int(dimension), C.byref(opt), ptr, C.byref(st)))
+    return out, st.as_dict()

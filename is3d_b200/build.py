@@ -22,6 +22,7 @@ SOURCES = [
     ("cf_kernels.cu", []),
     ("cf_factored.cu", []),
     ("cf_prepare.cu", ["-fmad=false"]),
+    ("cf_decays.cu", ["-fmad=false"]),
     ("cf_api.cu", []),
     ("host_math.cpp", []),
     ("host_io.cpp", []),

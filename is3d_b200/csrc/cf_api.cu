@@ -824,6 +824,53 @@ extern "C" int is3d_b200_mean_yield(const is3d_flags *fl, const is3d_surface *sf
 }
 
 
+// Resonance-decay feed-down: see cf_decays.cu
+extern "C" int is3d_b200_resonance_decays(const is3d_particle_list *pdg, int32_t n_chosen, const int32_t *chosen, const is3d_grid *gr,
+                                          int32_t dimension, const is3d_options *opt_in, double *dN, is3d_stats *stats)
+{
+  if (!pdg || !chosen || !gr || !dN || n_chosen <= 0) return fail(IS3D_ERR_ARGUMENT, "NULL argument");
+  if (dimension != 2 && dimension != 3) return fail(IS3D_ERR_ARGUMENT, "dimension must be 2 or 3");
+  if (!pdg->mcid || !pdg->mass || !pdg->width || !pdg->stable || !pdg->decays || !pdg->dec_first || !pdg->dec_npart || !pdg->dec_br || !pdg->dec_part)
+    return fail(IS3D_ERR_ARGUMENT, "incomplete particle list");
+  if (!gr->pT || !gr->phi || !gr->y || gr->n_pT <= 0 || gr->n_phi <= 0 || gr->n_y <= 0) return fail(IS3D_ERR_ARGUMENT, "momentum tables missing");
+  for (int i = 0; i < n_chosen; i++) if (chosen[i] < 0 || chosen[i] >= pdg->n_particles) return fail(IS3D_ERR_ARGUMENT, "chosen particle index out of range");
+  Device *Dp = nullptr;
+  { int rc = current_device(&Dp); if (rc) return rc; }
+  Workspace &ws = Dp->ws;
+  std::lock_guard<std::mutex> lk(Dp->mu);
+  is3d_options opt; memset(&opt, 0, sizeof(opt));
+  if (opt_in) opt = *opt_in;
+  cudaStream_t st = (cudaStream_t)opt.stream;
+  const int64_t n_bins = (int64_t)n_chosen * gr->n_pT * gr->n_phi * gr->n_y;
+  double *dev = dN;
+  cudaEvent_t *ev = ws.ev;
+  CU_CHECK(cudaEventRecord(ev[0], st));
+  if (opt.memory == 0) {
+    CU_CHECK(ws.dN.reserve((size_t)n_bins * 8 + 256));
+    dev = ws.dN.as<double>();
+    CU_CHECK(cudaMemcpyAsync(dev, dN, (size_t)n_bins * 8, cudaMemcpyHostToDevice, st));
+  }
+  CU_CHECK(cudaEventRecord(ev[1], st));
+  int launches = 0; std::string err;
+  const int rc = resonance_decays_device(pdg, n_chosen, chosen, gr, dimension, dev, st, &launches, &err);
+  if (rc != IS3D_OK) { cudaStreamSynchronize(st); return fail(rc, err.c_str()); }
+  CU_CHECK(cudaEventRecord(ev[2], st));
+  if (opt.memory == 0) CU_CHECK(cudaMemcpyAsync(dN, dev, (size_t)n_bins * 8, cudaMemcpyDeviceToHost, st));
+  CU_CHECK(cudaEventRecord(ev[3], st));
+  CU_CHECK(cudaEventSynchronize(ev[3]));
+  if (stats) {
+    is3d_stats stt; memset(&stt, 0, sizeof(stt));
+    float ms;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]); stt.h2d_ms = ms;
+    cudaEventElapsedTime(&ms, ev[1], ev[2]); stt.kernel_ms = ms;
+    cudaEventElapsedTime(&ms, ev[2], ev[3]); stt.d2h_ms = ms;
+    cudaEventElapsedTime(&ms, ev[0], ev[3]); stt.total_ms = ms;
+    stt.gpu_launches = launches; stt.n_gpus = 1;
+    *stats = stt;
+  }
+  return IS3D_OK;
+}
+
 // =====================================================================================================================
 // One process, several GPUs: contiguous cell shards, one host thread + stream per device, one NCCL all-reduce
 // =====================================================================================================================

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <string>
 #include "../../include/is3d_b200.h"
 
 namespace is3d {
@@ -104,6 +105,9 @@ cudaError_t launch_integ_reduce(const HotParams &hp, int n_units, double *out, c
 cudaError_t launch_yield(const RawCells &cells, const PrepTables &tab, int df_mode, int include_bulk, double *partial, int *n_blocks,
                          PrepCounters *counters, cudaStream_t st);
 cudaError_t launch_fp64_peak(double *sink, int iters, cudaStream_t st, int *blocks, int *threads, long long *dfma_per_thread);
+// resonance-decay feed-down on device-resident spectra (cf_decays.cu)
+int resonance_decays_device(const is3d_particle_list *pdg, int n_chosen, const int32_t *chosen, const is3d_grid *gr, int dimension,
+                            double *dN_dev, cudaStream_t st, int *launches, std::string *err);
 void hot_variant_shape(int variant, int dim2, int *nyt, int *npt, int *ct, int *max_warps);
 // factored kernel (cf_factored.cu): linear-df models, 3+1D tiles only
 constexpr int kNumVariants = 16;             // register-tile variants of cf_kernel (is3d_options.tile_variant 1..16)

@@ -119,14 +119,25 @@ static bool read_pdg_conventional(const std::string &path, std::vector<Particle>
     in >> p.mcid >> p.name >> p.mass >> p.width >> p.gspin >> p.baryon >> p.strange >> p.charm >> p.bottom >> p.gisospin >> p.charge >> p.decays;
     if (p.decays > 50) { if (err) *err = "too many decay channels in " + path; return false; }
     for (int j = 0; j < p.decays; j++) {
-      long id; int npart; double br; long d[5];
-      in >> id >> npart >> br >> d[0] >> d[1] >> d[2] >> d[3] >> d[4];
+      long id; DecayChannel ch;
+      in >> id >> ch.npart >> ch.branch_ratio >> ch.part[0] >> ch.part[1] >> ch.part[2] >> ch.part[3] >> ch.part[4];
+      p.channels.push_back(ch);
     }
+    p.stable = (!p.channels.empty() && p.channels[0].npart == 1) ? 1 : 0;      // readindata.cpp:1487-1488
     v.push_back(p);
     if (p.baryon > 0) {                                 // anti-baryon right behind its baryon (readindata.cpp:1491-1536)
       Particle a = p;
       a.mcid = -p.mcid; a.name = "Anti-baryon-" + p.name;
       a.baryon = -p.baryon; a.strange = -p.strange; a.charm = -p.charm; a.bottom = -p.bottom; a.charge = -p.charge;
+      // daughters: the anti-particle, unless the daughter is a neutral non-strange meson (its own anti-particle in this table);
+      // looked up among the particles read so far, first match (:1512-1530)
+      for (auto &ch : a.channels)
+        for (int k = 0; k < 5; k++) {
+          if (ch.part[k] == 0) continue;
+          bool neutral = false;
+          for (const auto &q : v) if (q.mcid == ch.part[k]) { neutral = (q.baryon == 0 && q.charge == 0 && q.strange == 0); break; }
+          if (!neutral) ch.part[k] = -ch.part[k];
+        }
       v.push_back(a);
     }
   }

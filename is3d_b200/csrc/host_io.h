@@ -29,11 +29,14 @@ struct BlockTable {
   double at(int col1, long row1) const { return cols[col1 - 1][row1 - 1]; }   // 1-based like Table::get
 };
 
+struct DecayChannel { int npart = 0; double branch_ratio = 0; long part[5] = {0, 0, 0, 0, 0}; };
 struct Particle {
   long mcid = 0;
   std::string name;
   double mass = 0, width = 0;
   int gspin = 0, baryon = 0, strange = 0, charm = 0, bottom = 0, gisospin = 0, charge = 0, decays = 0, sign = 0;
+  int stable = 0;                          // first channel has a single product (readindata.cpp:1487-1488)
+  std::vector<DecayChannel> channels;      // conventional lists only (pdg_box.dat carries no decay table)
 };
 // PDG/pdg-urqmd_v3.3+.dat, PDG/pdg_smash.dat (readindata.cpp:1440-1568) and PDG/pdg_box.dat (:1571-1684)
 bool read_pdg(const std::string &workdir, int hrg_eos, std::vector<Particle> *out, std::string *err);

@@ -115,6 +115,34 @@ static bool write_spectra_files(const std::string &wd, const std::vector<double>
   return true;
 }
 
+// results/dN_pTdpTdphidy_resonance_decays.dat and results/dN_dpTdphidy_resonance_decays.dat (append mode), as
+// write_dN_pTdpTdphidy_with_resonance_decays_toFile / write_dN_dpTdphidy_with_resonance_decays_toFile write them
+// (emissionfunction.cpp:452-488, 555-590): all species concatenated, the second file with a header and the values times pT
+static bool write_decay_files(const std::string &wd, const std::vector<double> &dN, int npart, const Grids &g, int dimension, std::string *err)
+{
+  const int npT = (int)g.pT.rows, nphi = (int)g.phi.rows, y_pts = (dimension == 2) ? 1 : (int)g.y.rows;
+  for (int which = 0; which < 2; which++) {
+    const std::string path = wd + (which == 0 ? "/results/dN_pTdpTdphidy_resonance_decays.dat" : "/results/dN_dpTdphidy_resonance_decays.dat");
+    std::ofstream f(path.c_str(), std::ios_base::app);
+    if (!f) { *err = "cannot open " + path; return false; }
+    if (which == 1) f << "y" << "\t" << "phip" << "\t" << "pT" << "\t" << "dN_dpTdphidy" << "\n";
+    for (int ipart = 0; ipart < npart; ipart++)
+      for (int iy = 0; iy < y_pts; iy++) {
+        const double y = (dimension == 2) ? 0.0 : g.y.at(1, iy + 1);
+        for (int iphi = 0; iphi < nphi; iphi++) {
+          for (int ipT = 0; ipT < npT; ipT++) {
+            const double pT = g.pT.at(1, ipT + 1);
+            double value = dN[(size_t)bin_index(ipart, npart, ipT, npT, iphi, nphi, iy)];
+            if (which == 1) value = value * pT;
+            f << std::scientific << std::setw(5) << std::setprecision(8) << y << "\t" << g.phi.at(1, iphi + 1) << "\t" << pT << "\t" << value << "\n";
+          }
+          f << "\n";
+        }
+      }
+  }
+  return true;
+}
+
 // results/spacetime_distribution/*.dat exactly as calculate_dN_dX{,_feqmod} write them (smooth_kernels.cpp:1112-1126, 1404-1435):
 // truncating opens, `setprecision(6) << scientific`, bin midpoints, sums divided by the bin volumes.
 static bool write_spacetime_files(const std::string &wd, const std::vector<int> &mcid, const is3d_spacetime_bins &b, int eta_pts,
@@ -152,7 +180,8 @@ static bool write_spacetime_files(const std::string &wd, const std::vector<int> 
 struct Problem {
   Params par;
   is3d_flags fl;
-  int operation = 0, hrg_eos = 0, group_particles = 0;
+  int operation = 0, hrg_eos = 0, group_particles = 0, do_resonance_decays = 0;
+  std::vector<int> pick;                   // particle-list index of every chosen species (chosen_particles_sampling_table)
   SurfaceData sf;
   std::vector<Particle> pdg;
   DfTables dft;
@@ -189,7 +218,9 @@ static int load_problem(const std::string &wd, bool need_surface, Problem *p, st
   fl.deta_min = par.get("deta_min", &err); fl.mass_pion0 = par.get("mass_pion0", &err);
   if (p->operation != 1 && p->operation != 0) { err = "this drop-in covers operation = 1 (smooth momentum spectra) and operation = 0 (spacetime distributions); the sampler (operation = 2) is out of scope"; return IS3D_ERR_UNSUPPORTED; }
   if (p->operation == 0 && fl.mode == 2) { err = "operation = 0 has no anisotropic-hydro routine in the reference (emissionfunction.cpp:1644-1673)"; return IS3D_ERR_UNSUPPORTED; }
-  if ((int)par.get("do_resonance_decays", &err)) { err = "do_resonance_decays = 1 is outside the smooth-spectra path"; return IS3D_ERR_UNSUPPORTED; }
+  p->do_resonance_decays = (int)par.get("do_resonance_decays", &err);
+  if (p->do_resonance_decays && p->operation != 1) { err = "do_resonance_decays = 1 applies to operation = 1 (the reference runs it after the spectra, emissionfunction.cpp:1689)"; return IS3D_ERR_UNSUPPORTED; }
+  if (p->do_resonance_decays && p->hrg_eos == 3) { err = "do_resonance_decays = 1 needs a particle list with decay tables (hrg_eos = 1, 2); pdg_box.dat has none"; return IS3D_ERR_UNSUPPORTED; }
 
   // ---- surface (+ averages side file)
   if (need_surface) {
@@ -222,6 +253,7 @@ static int load_problem(const std::string &wd, bool need_surface, Problem *p, st
     for (int m = 0; m < npart; m++)
       for (int n = 0; n < npart - m - 1; n++)
         if (p->pdg[pick[n]].mass > p->pdg[pick[n + 1]].mass) std::swap(pick[n], pick[n + 1]);
+  p->pick = pick;
   p->mass.resize(npart); p->sign.resize(npart); p->degen.resize(npart); p->baryon.resize(npart); p->mcid.resize(npart);
   for (int i = 0; i < npart; i++) {
     const Particle &h = p->pdg[pick[i]];
@@ -296,9 +328,31 @@ static int run_problem(const std::string &wd, Problem &P, const is3d_surface &s,
   if (rc != IS3D_OK) { err = std::string("spectra kernel failed: ") + is3d_b200_last_error(); return rc; }
   if (P.fl.mode != 2 && (P.fl.df_mode == 3 || P.fl.df_mode == 4))
     std::cout << std::setw(5) << std::setprecision(4) << "\nfeqmod breaks down for " << st.cells_feqmod_breakdown << " cells\n" << std::endl;
-  if (dN_raw) std::memcpy(dN_raw, dN.data(), sizeof(double) * (size_t)std::min<int64_t>(n_raw, (int64_t)n_bins));
   if (mcid_out) for (int i = 0; i < npart && i < n_mcid_max; i++) mcid_out[i] = P.mcid[i];
   if (!write_spectra_files(wd, dN, P.mcid, g, P.fl.dimension, &err)) return IS3D_ERR_IO;
+  if (P.do_resonance_decays) {
+    // feed-down on the GPU, then the two amended-spectra files (emissionfunction.cpp:1689-1698)
+    std::printf("Starting resonance decays: \n\n");
+    std::vector<int32_t> mcid, stable, decays, first, npartv, parts, chosen(P.pick.begin(), P.pick.end());
+    std::vector<double> mass, width, br;
+    for (const Particle &h : P.pdg) {
+      mcid.push_back((int32_t)h.mcid); mass.push_back(h.mass); width.push_back(h.width); stable.push_back(h.stable);
+      decays.push_back((int32_t)h.channels.size()); first.push_back((int32_t)npartv.size());
+      for (const DecayChannel &ch : h.channels) {
+        npartv.push_back(ch.npart); br.push_back(ch.branch_ratio);
+        for (int k = 0; k < 5; k++) parts.push_back((int32_t)ch.part[k]);
+      }
+    }
+    is3d_particle_list pl{(int32_t)P.pdg.size(), mcid.data(), mass.data(), width.data(), stable.data(), decays.data(), first.data(),
+                          npartv.data(), br.data(), parts.data()};
+    is3d_stats sd; std::memset(&sd, 0, sizeof(sd));
+    const int rcd = is3d_b200_resonance_decays(&pl, npart, chosen.data(), &gr, P.fl.dimension, nullptr, dN.data(), &sd);
+    if (rcd != IS3D_OK) { err = std::string("resonance decays failed: ") + is3d_b200_last_error(); return rcd; }
+    std::printf("\n\nResonance decays took %f seconds.\n", sd.total_ms * 1e-3);
+    if (stats) { stats->gpu_launches += sd.gpu_launches; stats->total_ms += sd.total_ms; }
+    if (!write_decay_files(wd, dN, npart, g, P.fl.dimension, &err)) return IS3D_ERR_IO;
+  }
+  if (dN_raw) std::memcpy(dN_raw, dN.data(), sizeof(double) * (size_t)std::min<int64_t>(n_raw, (int64_t)n_bins));
   return IS3D_OK;
 }
 
@@ -395,6 +449,12 @@ extern "C" int is3d_b200_host_dump(const char *workdir, const char *out_path)
   tmp.clear(); for (auto &h : P.pdg) tmp.push_back(h.gspin); put("pdg_gspin", tmp);
   tmp.clear(); for (auto &h : P.pdg) tmp.push_back(h.sign); put("pdg_sign", tmp);
   tmp.clear(); for (auto &h : P.pdg) tmp.push_back(h.baryon); put("pdg_baryon", tmp);
+  // decay tables (resonance-decay feed-down): stable flag, channels per particle, flattened channel rows
+  tmp.clear(); for (auto &h : P.pdg) tmp.push_back(h.stable); put("pdg_stable", tmp);
+  tmp.clear(); for (auto &h : P.pdg) tmp.push_back((double)h.channels.size()); put("pdg_decays", tmp);
+  tmp.clear(); for (auto &h : P.pdg) for (auto &ch : h.channels) tmp.push_back(ch.npart); put("pdg_dec_npart", tmp);
+  tmp.clear(); for (auto &h : P.pdg) for (auto &ch : h.channels) tmp.push_back(ch.branch_ratio); put("pdg_dec_br", tmp);
+  tmp.clear(); for (auto &h : P.pdg) for (auto &ch : h.channels) for (int k = 0; k < 5; k++) tmp.push_back((double)ch.part[k]); put("pdg_dec_part", tmp);
   const SurfaceData &s = P.sf;
   put("tau", s.tau); put("eta", s.eta); put("dat", s.dat); put("dax", s.dax); put("day", s.day); put("dan", s.dan);
   put("ux", s.ux); put("uy", s.uy); put("un", s.un); put("E", s.E); put("T", s.T); put("P", s.P);

@@ -47,6 +47,46 @@ def pdg_table(fx, hrg_eos):
                 baryon=np.array(baryon, dtype=np.int64), sign=np.array(sign, dtype=np.int64))
 
 
+def pdg_decay_table(fx, hrg_eos):
+    """The reference's particle_info array incl. decay channels (readindata.cpp:1440-1568, hrg_eos 1 / 2): anti-baryons right behind
+    their baryon with the daughters' ids negated unless the daughter is a neutral non-strange meson (:1512-1530); `stable` when the
+    first channel has one product (:1487-1488).  Channels are flattened: rows dec_first[i] .. dec_first[i] + decays[i]."""
+    key = _PDG_KEY[hrg_eos]
+    g = lambda k: fx["%s/%s" % (key, k)]
+    owner = g("dec_owner"); dn = g("dec_n"); br = g("dec_br"); parts = g("dec_parts")
+    first = np.searchsorted(owner, np.arange(len(g("mcid"))))
+    out = dict(mcid=[], mass=[], width=[], baryon=[], charge=[], strange=[], stable=[], decays=[], dec_first=[], dec_npart=[], dec_br=[], dec_part=[])
+
+    def push(mcid, i, b, q, s, chans):
+        out["mcid"].append(int(mcid)); out["mass"].append(float(g("mass")[i])); out["width"].append(float(g("width")[i]))
+        out["baryon"].append(b); out["charge"].append(q); out["strange"].append(s)
+        out["stable"].append(1 if (chans and chans[0][0] == 1) else 0)
+        out["decays"].append(len(chans)); out["dec_first"].append(len(out["dec_npart"]))
+        for n_, b_, p_ in chans:
+            out["dec_npart"].append(int(n_)); out["dec_br"].append(float(b_)); out["dec_part"].append([int(v) for v in p_])
+
+    for i in range(len(g("mcid"))):
+        chans = [(int(dn[j]), float(br[j]), [int(v) for v in parts[j]]) for j in range(first[i], first[i] + int(g("decays")[i]))]
+        b, q, s = int(g("baryon")[i]), int(g("charge")[i]), int(g("strange")[i])
+        push(g("mcid")[i], i, b, q, s, chans)
+        if b > 0:
+            anti = []
+            for n_, b_, p_ in chans:
+                pp = []
+                for v in p_:
+                    if v == 0:
+                        pp.append(0); continue
+                    try:
+                        idx = out["mcid"].index(v)                       # first match among the particles read so far
+                        neutral = out["baryon"][idx] == 0 and out["charge"][idx] == 0 and out["strange"][idx] == 0
+                    except ValueError:
+                        neutral = False                                  # the reference reads one past the list here
+                    pp.append(v if neutral else -v)
+                anti.append((n_, b_, pp))
+            push(-int(g("mcid")[i]), i, -b, -q, -s, anti)
+    return {k: np.asarray(v) for k, v in out.items()}
+
+
 def species(fx, hrg_eos=1, chosen="chosen_urqmd", group_particles=False):
     pdg = pdg_table(fx, hrg_eos)
     ids = fx[chosen] if isinstance(chosen, str) else np.asarray(chosen, dtype=np.int64)

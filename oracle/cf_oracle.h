@@ -6,8 +6,10 @@
  * Parity status: PINNED for df_mode 1-4 (mode 1 surfaces, 3+1D and 2+1D) against the unmodified reference sources
  * compiled here (oracle/_ref/is3d_ref, see oracle/Makefile) -- tests/test_oracle_vs_reference.py and the committed
  * vectors under tests/golden/.  The anisotropic kernel (cf_oracle_smooth_vah) is pinned against a direct call of the
- * reference's (otherwise uncalled) calculate_dN_pTdpTdphidy_VAH_PL; its coefficient lookup follows the only
- * specification that exists (src/cuda/deltafReader.cu:192-277) and is "parity unpinned".
+ * reference's (otherwise uncalled) calculate_dN_pTdpTdphidy_VAH_PL; its (Lambda, alpha_L) coefficient lookup is pinned against
+ * the reference's only reader of those tables, src/cuda/deltafReader.cu:192-277, compiled into oracle/_ref/vah_ref
+ * (tests/golden/vah_coefficients.npz).  The resonance-decay routine (cf_decays.c) is pinned against the reference's routine run
+ * behind oracle/ref_decays_prefix.h (its author disabled it with an exit(-1) at entry).
  * GSL is absent from the image: the natural cubic spline and the 3x3 LU inverse restate GSL's published
  * algorithms (see oracle/gsl_shim); "parity unpinned" against a real libgsl at the 1e-16 level.
  */
@@ -121,6 +123,18 @@ int cfo_particle_densities(int n, const double *mass, const double *degeneracy, 
                            const double *root3, const double *weight3, double *neq_out, double *bulk_out, double *diff_out);
 int64_t cfo_total_yield(const cfo_flags *fl, const cfo_cells *c, int n_species, const double *neq, const double *bulk,
                         const cfo_df_tables *tab, double y_cut, double *Ntot_out);
+
+/* Resonance-decay feed-down: EmissionFunctionArray::do_resonance_decays and everything below it,
+ * emissionfunction_resonance_decays.cpp:124-2158 (oracle/cf_decays.c).  The particle list is the reference's particle_info array
+ * (readindata.cpp:1440-1568: anti-baryons synthesised, decay channels flattened: channel rows dec_first[i] .. + decays[i]).
+ * dN [y][phi][pT][chosen species] is amended in place; returns 0 or a negative error code (the reference exits there). */
+typedef struct {
+  int32_t n_particles;
+  const int32_t *mcid; const double *mass, *width; const int32_t *stable, *decays, *dec_first;
+  const int32_t *dec_npart; const double *dec_br; const int32_t *dec_part;       /* dec_part[row * 5 + k] */
+} cfo_particles;
+int cfo_resonance_decays(const cfo_particles *pdg, int32_t n_chosen, const int32_t *chosen_pdg_index, const cfo_grid *g, int32_t dimension,
+                         double *dN);
 
 /* VAH helpers: aL_fit / R200 (arsenal.cpp:999-1066) and the (Lambda, aL) bilinear lookup of
  * src/cuda/deltafReader.cu:192-277 */

@@ -305,3 +305,54 @@ def run_vah_reference(aL, Lambda_GeV, fixture=None):
         if r.returncode != 0:
             raise RuntimeError("vah_ref failed: %s" % r.stderr[-1000:])
         return np.fromfile(os.path.join(wd, "out.bin")).reshape(len(aL), 5)
+
+
+# --------------------------------------------------------------------------- resonance decays
+class Particles(C.Structure):
+    _I = C.POINTER(C.c_int32)
+    _fields_ = [("n_particles", C.c_int32), ("mcid", _I), ("mass", _D), ("width", _D), ("stable", _I), ("decays", _I), ("dec_first", _I),
+                ("dec_npart", _I), ("dec_br", _D), ("dec_part", _I)]
+
+
+def resonance_decays(pdg, chosen_pdg_index, grid, dimension, dN):
+    """cfo_resonance_decays: pdg = dict from is3d_b200.tables.pdg_decay_table(); returns the amended copy of dN."""
+    keep = []
+
+    def ia(x):
+        a = np.ascontiguousarray(x, dtype=np.int32); keep.append(a)
+        return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+    def da(x):
+        a = np.ascontiguousarray(x, dtype=np.float64); keep.append(a)
+        return a.ctypes.data_as(_D)
+
+    p = Particles()
+    p.n_particles = len(pdg["mcid"])
+    p.mcid = ia(pdg["mcid"]); p.mass = da(pdg["mass"]); p.width = da(pdg["width"]); p.stable = ia(pdg["stable"]); p.decays = ia(pdg["decays"])
+    p.dec_first = ia(pdg["dec_first"]); p.dec_npart = ia(pdg["dec_npart"]); p.dec_br = da(pdg["dec_br"]); p.dec_part = ia(np.asarray(pdg["dec_part"]).ravel())
+    k = _Keep(); g = _grid(k, grid)
+    out = np.array(dN, dtype=np.float64, copy=True)
+    f = lib().cfo_resonance_decays
+    f.restype = C.c_int
+    rc = f(C.byref(p), C.c_int32(len(chosen_pdg_index)), ia(chosen_pdg_index), C.byref(g), C.c_int32(dimension), _p(out))
+    if rc:
+        raise RuntimeError("cf_oracle resonance decays error %d" % rc)
+    return out
+
+
+def run_reference_decays(workdir_path, dN_in, timeout=3600):
+    """oracle/_ref/is3d_ref_decays (the reference's do_resonance_decays behind oracle/ref_decays_prefix.h) on the spectra dN_in inside a
+    materialised working directory; returns (amended spectra, info)."""
+    exe = os.path.join(_HERE, "_ref", "is3d_ref_decays")
+    if not os.path.exists(exe):
+        raise FileNotFoundError("oracle/_ref/is3d_ref_decays not built (run `make -C oracle ref` where /root/reference exists)")
+    np.ascontiguousarray(dN_in, dtype=np.float64).tofile(os.path.join(workdir_path, "input", "spectra_in.bin"))
+    out = os.path.join(workdir_path, "results", "dN_decays.bin")
+    r = subprocess.run([exe, "decays", out], cwd=workdir_path, capture_output=True, text=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError("reference decays failed (%d): %s\n%s" % (r.returncode, r.stdout[-2000:], r.stderr[-2000:]))
+    info = None
+    for line in r.stdout.splitlines():
+        if line.startswith("REF_JSON "):
+            info = json.loads(line[len("REF_JSON "):])
+    return np.fromfile(out), info
