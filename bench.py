@@ -57,6 +57,7 @@ def parse():
                     help="1: momentum spectra (headline); 0: spacetime distributions of the same integrand (SURVEY 8f N2), df_mode 1-4 workloads")
     ap.add_argument("--cells", type=int, default=0, help="override the cell count (development only; reported in config)")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--chunks", type=int, default=0, help="cell chunks per launch (0 = library default; 1 makes every block stream the whole surface)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--single-process", action="store_true",
@@ -199,7 +200,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------ roofline helpers
 # FP64-pipe instructions executed per evaluation (warp instructions per warp-evaluation, dead evaluations included), from the
 # committed ncu captures of the default kernel of each model (profiles/README.md names the file behind every number)
-FP64_INSTR_PER_EVAL = {1: 17.76, 2: 21.9, 3: 22.6, 4: 22.6, 5: 21.0, "ideal2d": 9.4}
+FP64_INSTR_PER_EVAL = {1: 17.76, 2: None, 3: 22.6, 4: 22.6, 5: None, "ideal2d": None}
 
 
 def alive_fraction(cells, sp, g, dim, n_sample=256, vah=False):
@@ -385,7 +386,7 @@ def main():
         if spacetime:
             return spacetime_step(dev, "device")
         out.zero_()
-        _, st = api.smooth_spectra(fl, dev, sp, g, tab, gla, out=out, memory="device", tile_variant=args.variant)
+        _, st = api.smooth_spectra(fl, dev, sp, g, tab, gla, out=out, memory="device", tile_variant=args.variant, n_chunks=args.chunks)
         if world > 1:
             dist.all_reduce(out, op=dist.ReduceOp.SUM)
         return st

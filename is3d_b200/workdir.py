@@ -3,7 +3,7 @@
 iS3D (and this drop-in) read every input from CWD-relative paths (reference src/cpp/iS3D.cpp:83,156-167;
 deltafReader.h:27-29; readindata.h:217-219).  `materialize()` writes those files -- parameter file, particle
 lists, quadrature tables, delta-f coefficient tables, surface -- into a directory, using the same text formats the
-reference's readers expect, from `tests/golden/is3d_tables.npz` (numeric content extracted once by
+reference's readers expect, from `is3d_b200/data/is3d_tables.npz` (numeric content extracted once by
 tests/golden/make_tables_fixture.py).  Numbers are written with repr(), which round-trips every double exactly.
 
 This is tooling for tests / benchmarks / the smoke test; the product's C++ host layer (csrc/host_*.cpp) only ever
@@ -13,7 +13,7 @@ import os
 
 import numpy as np
 
-_FIXTURE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "is3d_tables.npz")
+_FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "is3d_tables.npz")
 
 # every key the reference constructor getVal()s (emissionfunction.cpp:170-222, readindata.cpp:111-118,
 # deltafReader.cpp:24-27, iS3D.cpp:164); a missing key is fatal there, so the template carries all of them.

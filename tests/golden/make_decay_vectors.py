@@ -32,8 +32,9 @@ def case_inputs(fx, rec):
     """(grid dict, table overrides, surface columns, thermal spectra from the oracle, particle list, chosen particle-list indices)"""
     tabs = None
     if rec["strides"]:
-        s = rec["strides"]
-        tabs = dict(pT=fx["pT_tab"][::s["pT"]], phi=fx["phi_tab"][::s["phi"]], y=fx["y_tab"][::s["y"]])
+        s = rec["strides"]                                   # an int = stride, a list = explicit row indices
+        pick = lambda t, v: t[::v] if isinstance(v, int) else t[list(v)]
+        tabs = dict(pT=pick(fx["pT_tab"], s["pT"]), phi=pick(fx["phi_tab"], s["phi"]), y=pick(fx["y_tab"], s["y"]))
     g = tables.grid(fx, tabs)
     cols = synthetic.surface_vh(rec["n_cells"], rec["seed"], three_d=(rec["dimension"] == 3))
     cells = synthetic.columns_to_cells(cols, 1)

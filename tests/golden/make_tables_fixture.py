@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Build tests/golden/is3d_tables.npz from the reference checkout's DATA files (not sources).
+"""Build is3d_b200/data/is3d_tables.npz from the reference checkout's DATA files (not sources).
 
 Run in the build container, where /root/reference exists:
     python tests/golden/make_tables_fixture.py [/root/reference]
@@ -131,7 +131,7 @@ def main():
     for k, v in read_df_vah(os.path.join(ref, "deltaf_coefficients/vah")).items():
         fx["df_vah/%s" % k] = v
     fx["toy_surface"] = read_table(os.path.join(ref, "input/surface.dat"))
-    out = os.path.join(here, "is3d_tables.npz")
+    out = os.path.join(os.path.dirname(os.path.dirname(here)), "is3d_b200", "data", "is3d_tables.npz")
     np.savez_compressed(out, **fx)
     print("wrote", out, os.path.getsize(out), "bytes;", len(fx), "arrays")
 

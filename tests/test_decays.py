@@ -108,17 +108,30 @@ def test_cuda_decays_match_reference_vectors(fx, name):
 
 
 @pytest.mark.gpu
-def test_cuda_decays_full_species_list_against_oracle(fx):
-    """the whole 305-species list (every parent, channel and anti-baryon of pdg-urqmd_v3.3+) on a reduced momentum grid, 2+1D and 3+1D"""
+def test_cuda_decays_long_species_lists_against_oracle(fx):
+    """the first 150 (2+1D) / 70 (3+1D) species of the 305-species list on reduced momentum grids: ~600 channels incl. anti-baryon
+    parents, mass-shifted 2-body channels and 3-body channels.  With these lists the reference's arithmetic makes the nucleon bins NaN
+    (a channel whose daughter energy in the parent frame falls below its mass: sqrt of a negative number, :415-416) -- same bins
+    here; with the whole list the reference then stops in its large-mT fit ("not enough points"), as does this library (error code)."""
     api.init()
-    for dim, strides in ((2, dict(pT=2, phi=2, y=1)), (3, dict(pT=4, phi=4, y=5))):
-        rec = dict(dimension=dim, n_cells=30, seed=11, strides=strides, chosen=[int(v) for v in fx["chosen_urqmd"]])
+    full = [int(v) for v in fx["chosen_urqmd"]]
+    hi_pT = list(range(0, 22, 3)) + list(range(22, 32))            # every parent needs >= 2 points beyond mT = 1.65 M for its tail fit
+    for dim, strides, k in ((2, dict(pT=hi_pT, phi=3, y=1), 150), (3, dict(pT=hi_pT, phi=4, y=[7, 9, 10, 11, 13]), 70)):
+        rec = dict(dimension=dim, n_cells=30, seed=11, strides=strides, chosen=full[:k])
         g, tabs, cols, dN, pdg, chosen_idx = mdv.case_inputs(fx, rec)
         ref = cfo.resonance_decays(pdg, chosen_idx, g, dim, dN)
         got, st = api.resonance_decays(pdg, chosen_idx, g, dim, dN)
-        max_rel, zeros, nans = _compare(got, ref)
-        print("dim", dim, "max rel %.3e" % max_rel, "kernel ms %.1f" % st["kernel_ms"])
-        assert nans == int(np.isnan(ref).sum()) and max_rel <= REL_TOL, (dim, max_rel)
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        fin = ~np.isnan(ref)
+        max_rel, zeros, _ = _compare(got[fin], ref[fin])
+        print("dim", dim, "species", k, "max rel %.3e" % max_rel, "NaN bins", int((~fin).sum()), "kernel ms %.1f" % st["kernel_ms"])
+        assert zeros and max_rel <= REL_TOL, (dim, max_rel)
+    # the whole list: the reference exits in estimate_MT_function_of_dNdypTdpTdphi (:2078-2082); here an error code
+    rec = dict(dimension=2, n_cells=30, seed=11, strides=dict(pT=hi_pT, phi=3, y=1), chosen=full)
+    g, tabs, cols, dN, pdg, chosen_idx = mdv.case_inputs(fx, rec)
+    with pytest.raises(api.Is3dError) as e:
+        api.resonance_decays(pdg, chosen_idx, g, 2, dN)
+    assert e.value.code == 1
 
 
 @pytest.mark.gpu
