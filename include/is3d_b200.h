@@ -91,7 +91,9 @@ typedef struct {
   int32_t memory;            /* 0: surface arrays and dN live in host memory; 1: they are device pointers on the current device */
   void *stream;              /* cudaStream_t to launch on (NULL = default stream) */
   int32_t n_chunks;          /* cell-range split used for load balance; 0 = choose */
-  int32_t tile_variant;      /* kernel register-tile variant: 0 = tuned default for the model, k = 1..16 selects table entry k - 1 */
+  int32_t tile_variant;      /* kernel register-tile variant: 0 = tuned default for the model, k = 1..16 selects table entry k - 1,
+                                17..21 = shapes of the factored kernel (df_mode 1/2, 3+1D, >= 16 species), 99 = strict diagnostic kernel
+                                (df_mode 1/2 in the reference's own operation order, one thread per bin: ~50x slower, tests only) */
   int32_t reserved[4];
 } is3d_options;
 
@@ -104,6 +106,8 @@ typedef struct {
   int32_t n_chunks, tile_variant;
   int32_t n_gpus;                  /* devices that worked on this call (times above: slowest device) */
   double allreduce_ms;             /* multi-GPU: the NCCL all-reduce of the spectra array */
+  int32_t n_chunks_wanted;         /* chunks the load-balance rule asked for; > n_chunks when the 2 GiB partial-sum cap cut it down */
+  int32_t reserved;
 } is3d_stats;
 
 /* Bind to the current CUDA device and create its workspace (one per CUDA ordinal).  Safe to call more than once. */

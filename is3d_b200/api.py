@@ -60,7 +60,8 @@ class Stats(C.Structure):
     _fields_ = [("cells_skipped_udsigma", C.c_int64), ("cells_feqmod_breakdown", C.c_int64), ("evaluations", C.c_int64),
                 ("h2d_ms", C.c_double), ("prepare_ms", C.c_double), ("kernel_ms", C.c_double), ("reduce_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("total_ms", C.c_double), ("gpu_launches", C.c_int32), ("n_chunks", C.c_int32),
-                ("tile_variant", C.c_int32), ("n_gpus", C.c_int32), ("allreduce_ms", C.c_double)]
+                ("tile_variant", C.c_int32), ("n_gpus", C.c_int32), ("allreduce_ms", C.c_double),
+                ("n_chunks_wanted", C.c_int32), ("reserved", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

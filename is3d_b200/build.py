@@ -23,6 +23,7 @@ SOURCES = [
     ("cf_factored.cu", []),
     ("cf_prepare.cu", ["-fmad=false"]),
     ("cf_decays.cu", ["-fmad=false"]),
+    ("cf_strict.cu", ["-fmad=false"]),
     ("cf_api.cu", []),
     ("host_math.cpp", []),
     ("host_io.cpp", []),

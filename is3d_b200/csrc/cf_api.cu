@@ -271,7 +271,6 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   const bool dim2 = (fl->dimension == 2);
   const int64_t n_bins = (int64_t)sp->n * gr->n_pT * gr->n_phi * gr->n_y;
 
-  const bool dim2_early = (fl->dimension == 2);
   // ---- layout
   Layout L; memset(&L, 0, sizeof(L));
   L.n_species = sp->n; L.n_pT = gr->n_pT; L.n_phi = gr->n_phi; L.n_y_out = gr->n_y;
@@ -288,8 +287,12 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   // 17..21 = shapes of the factored kernel (cf_factored.cu; linear-df models on 3+1D tiles, >= 16 species): opt-in for the main
   // pass (measured within +-10 % of cf_kernel on B200), always used for the sparse linear-branch pass of
   // df_mode 3 / 4, where its per-cell skip of dead records makes that pass nearly free
+  // 99 = strict diagnostic variant (cf_strict.cu): df_mode 1 / 2 spectra in the reference's operation order, one thread per bin
   int variant, fvariant = -1;
   const bool f_ok = factored_supported(model, L) && !iq;      // operation = 0 integrates over the pT lanes of a block (cf_kernel)
+  const bool strict = (opt.tile_variant == kStrictVariant);
+  if (strict && (iq || vah || feqmod)) return fail(IS3D_ERR_ARGUMENT, "tile_variant 99 (strict diagnostic kernel) needs df_mode 1/2, mode 1 and operation 1");
+  if (opt.tile_variant < 0 || (opt.tile_variant > kNumVariants + kNumFactoredVariants && !strict)) return fail(IS3D_ERR_ARGUMENT, "unknown tile_variant");
   if (opt.tile_variant >= 1 && opt.tile_variant <= kNumVariants) variant = opt.tile_variant - 1;
   else if (opt.tile_variant > kNumVariants && opt.tile_variant <= kNumVariants + kNumFactoredVariants) {
     if (!f_ok) return fail(IS3D_ERR_ARGUMENT, "tile_variant 17..21 (factored kernel) needs df_mode 1/2, dimension 3, operation 1 and >= 16 species");
@@ -346,9 +349,11 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   if (fvariant >= 0) factored_blocking(sp->n, gr->n_pT, L.n_ptiles, &n_warps, &n_groupblocks);   // lanes = species, warps = phi tiles
   const int64_t n_bintiles = (int64_t)n_groupblocks * L.n_ytiles * (fvariant >= 0 ? 1 : L.n_ptiles);      // blocks per cell chunk
   int n_chunks = opt.n_chunks;
+  int n_chunks_wanted = n_chunks;
   if (n_chunks <= 0) {
     const int64_t target_blocks = (int64_t)g_sm_count * 96;             // >= 16 waves at 6 blocks/SM: small tail
     n_chunks = (int)((target_blocks + n_bintiles - 1) / n_bintiles);
+    n_chunks_wanted = n_chunks;                                         // reported next to the capped value (is3d_stats)
     const int64_t max_partial_bytes = (int64_t)2 << 30;                 // keep the partial buffer <= 2 GiB
     int64_t cap = max_partial_bytes / (n_bins * 8 > 0 ? n_bins * 8 : 1);
     if (feqmod) cap /= 2;
@@ -357,6 +362,7 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   }
   if ((int64_t)n_chunks > L.n_tiles) n_chunks = (int)(L.n_tiles > 0 ? L.n_tiles : 1);
   if (n_chunks < 1) n_chunks = 1;
+  if ((int64_t)n_chunks_wanted > L.n_tiles) n_chunks_wanted = n_chunks;   // fewer cell tiles than chunks is not a cap
   // operation = 0, mode 1: a chunk never crosses a category; large categories are split into chunks of ~ n_tiles / n_chunks tiles
   std::vector<int64_t> gather_h, chunk_tiles_h;
   const int integ_sl = (n_warps * 32 - 1) / gr->n_pT + 2;
@@ -517,7 +523,12 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   tab.deta_min = fl->deta_min; tab.mass_pion0 = fl->mass_pion0;
   tab.eta_delta = (dim2 && gr->n_eta > 1) ? gr->eta[1] - gr->eta[0] : 0.0;                    // smooth_kernels.cpp:2175
   PrepCounters *cnt_d = g_ws.counters.as<PrepCounters>();
-  if (vah) {
+  if (strict) {
+    CU_CHECK(g_ws.Y.reserve((size_t)n_cells * strict_cell_bytes() + 256));
+    CU_CHECK(launch_strict(*fl, rc, tab, L, dptr(o_mass), dptr(o_sign), dptr(o_deg), dptr(o_pT), dim2 ? gr->n_eta : 1,
+                           pow(2.0 * M_PI * 0.197327053, -3), g_ws.Y.p, dN_dev, cnt_d, st));
+    stt.gpu_launches += 2;
+  } else if (vah) {
     CU_CHECK(launch_prepare_vah(*fl, rc, tab, L, g_ws.Y.as<double>(), g_ws.P.as<double>(), g_ws.S.as<double>(), cnt_d, st));
     stt.gpu_launches++;
   } else if (feqmod) {
@@ -557,9 +568,10 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
     hp.integ_mode = iq->mode; hp.integ_sl = integ_sl; hp.chunk_tiles = chunk_tiles_d;
     hp.pT_weight = wpT_d; hp.phi_weight = wphi_d; hp.integ = g_ws.integ.as<double>();
   }
-  if (fvariant >= 0) CU_CHECK(launch_factored(model, hp, fvariant, st, nullptr));
+  if (strict) {}                                              // the bins were summed by launch_strict above
+  else if (fvariant >= 0) CU_CHECK(launch_factored(model, hp, fvariant, st, nullptr));
   else CU_CHECK(launch_hot(model, hp, variant, st, nullptr));
-  stt.gpu_launches++;
+  if (!strict) stt.gpu_launches++;
   int reduce_sets = 1;
   if (feqmod) {
     // cells where feqmod breaks down (and narrow-rapidity slots) take the linear-df branch: second pass, only if any
@@ -593,7 +605,7 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
       CU_CHECK(launch_integ_reduce(hl, iq->n_units, g_ws.integ_out.as<double>() + unit_vals, st));
       stt.gpu_launches++;
     }
-  } else {
+  } else if (!strict) {
     CU_CHECK(launch_reduce(hp.partial, n_chunks * reduce_sets, n_bins, dim2 ? n_bins / gr->n_y : n_bins, dN_dev, st));
     stt.gpu_launches++;
   }
@@ -631,7 +643,8 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   stt.cells_skipped_udsigma = (int64_t)cnt.skipped;
   stt.cells_feqmod_breakdown = (int64_t)cnt.breakdown;
   stt.evaluations = n_cells * (int64_t)sp->n * gr->n_pT * gr->n_phi * (dim2 ? (int64_t)gr->n_eta : (int64_t)gr->n_y);
-  stt.n_chunks = n_chunks; stt.tile_variant = variant;
+  stt.n_chunks = n_chunks; stt.tile_variant = strict ? kStrictVariant - 1 : variant;
+  stt.n_chunks_wanted = n_chunks_wanted;
   stt.n_gpus = 1;
   if (stats) *stats = stt;
   return IS3D_OK;
@@ -949,7 +962,7 @@ static void merge_stats(is3d_stats *acc, const is3d_stats &s)
   acc->h2d_ms = std::max(acc->h2d_ms, s.h2d_ms); acc->prepare_ms = std::max(acc->prepare_ms, s.prepare_ms);
   acc->kernel_ms = std::max(acc->kernel_ms, s.kernel_ms); acc->reduce_ms = std::max(acc->reduce_ms, s.reduce_ms);
   acc->d2h_ms = std::max(acc->d2h_ms, s.d2h_ms); acc->total_ms = std::max(acc->total_ms, s.total_ms);
-  acc->n_chunks = s.n_chunks; acc->tile_variant = s.tile_variant;
+  acc->n_chunks = s.n_chunks; acc->tile_variant = s.tile_variant; acc->n_chunks_wanted = s.n_chunks_wanted;
 }
 
 }  // namespace is3d

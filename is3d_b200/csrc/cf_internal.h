@@ -108,6 +108,12 @@ cudaError_t launch_fp64_peak(double *sink, int iters, cudaStream_t st, int *bloc
 // resonance-decay feed-down on device-resident spectra (cf_decays.cu)
 int resonance_decays_device(const is3d_particle_list *pdg, int n_chosen, const int32_t *chosen, const is3d_grid *gr, int dimension,
                             double *dN_dev, cudaStream_t st, int *launches, std::string *err);
+// strict (reference-order) diagnostic variant, df_mode 1 / 2 (cf_strict.cu); cell_scratch: n_cells * strict_cell_bytes()
+size_t strict_cell_bytes();
+cudaError_t launch_strict(const is3d_flags &fl, const RawCells &cells, const PrepTables &tab, const Layout &L, const double *mass, const double *sign,
+                          const double *degeneracy, const double *pT, int n_eta, double prefactor, void *cell_scratch, double *dN_dev,
+                          PrepCounters *counters, cudaStream_t st);
+constexpr int kStrictVariant = 99;           // is3d_options.tile_variant value that selects it
 void hot_variant_shape(int variant, int dim2, int *nyt, int *npt, int *ct, int *max_warps);
 // factored kernel (cf_factored.cu): linear-df models, 3+1D tiles only
 constexpr int kNumVariants = 16;             // register-tile variants of cf_kernel (is3d_options.tile_variant 1..16)

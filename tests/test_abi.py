@@ -31,7 +31,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(api.Species) == 8 + 8 * 4
     assert ctypes.sizeof(api.Grid) == 16 + 8 * 5
     assert ctypes.sizeof(api.Options) == 4 + 4 + 8 + 4 + 4 + 16
-    assert ctypes.sizeof(api.Stats) == 3 * 8 + 6 * 8 + 4 * 4 + 8      # ... + n_gpus, allreduce_ms
+    assert ctypes.sizeof(api.Stats) == 3 * 8 + 6 * 8 + 4 * 4 + 8 + 8  # ... + n_gpus, allreduce_ms, n_chunks_wanted, reserved
 
 
 def test_error_strings():

@@ -196,6 +196,62 @@ def test_sampled_bins_against_oracle_at_full_species(big, fx):
     assert rep["ok"], rep
 
 
+@pytest.mark.parametrize("df_mode", [1, 2])
+def test_ill_conditioned_bins_strict_variant(big, fx, df_mode):
+    """tile_variant 99 evaluates every term in the reference's own operation order (cf_strict.cu: no hoisting, no factorisation,
+    cosh / sinh / exp / divisions per evaluation, -fmad=false); all that separates it from the oracle is the device libm (<= 2 ulp).
+    In the well-conditioned bins it therefore sits at ~1e-15 from the oracle -- and in the handful of bins where the restructured
+    kernel exceeds 1e-10 it moves by 1e-11 or more as well: those bins are uncertain in the reference's own arithmetic, which
+    is what the conditioning allowance of common.compare encodes."""
+    from oracle import cf_oracle as cfo
+    cells, dev, sp, g, tab = big
+    sub = {k: v[:64] for k, v in cells.items()}
+    fl = tables.flags(df_mode=df_mode, dimension=3)
+    cond = np.zeros(305 * 32 * 24 * 21)
+    ref, _, _ = cfo.smooth(fl, sub, sp, g, tab, None, conditioning=cond)
+    fast, _ = api.smooth_spectra(fl, sub, sp, g, tab, None)
+    strict, st = api.smooth_spectra(fl, sub, sp, g, tab, None, tile_variant=99)
+    assert st["tile_variant"] == 98 and st["gpu_launches"] == 2
+    nz = ref != 0
+    assert np.all(strict[~nz] == 0)
+    rel_fast = np.abs(fast[nz] - ref[nz]) / np.abs(ref[nz])
+    rel_strict = np.abs(strict[nz] - ref[nz]) / np.abs(ref[nz])
+    amp = cond[nz] / np.abs(ref[nz])                                 # conditioning of the bin: sum |terms| / |sum|
+    well = amp < 10.0
+    print("df_mode %d: well-conditioned bins %d, strict max rel %.3g, fast max rel %.3g" % (df_mode, well.sum(), rel_strict[well].max(), rel_fast[well].max()))
+    assert rel_strict[well].max() < 1e-12 and rel_fast[well].max() < REL_TOL
+    assert compare(strict, ref, conditioning=cond)["ok"]
+    bad = np.flatnonzero(rel_fast > REL_TOL)
+    print("bins where the restructured kernel exceeds 1e-10: %d" % bad.size)
+    for b in bad:
+        print("  amplification %.3g  fast %.3g  strict %.3g" % (amp[b], rel_fast[b], rel_strict[b]))
+    if bad.size:
+        assert np.all(amp[bad] > 1e3)
+        # the reference-order evaluation moves in the same bins: at least 1e4 x its own well-conditioned deviation
+        assert np.median(rel_strict[bad]) > 1e4 * np.median(rel_strict[well][rel_strict[well] > 0]), (rel_strict[bad], np.median(rel_strict[well]))
+    # and the two evaluations are each other's peers in the ill-conditioned bins: same order of magnitude of noise per unit of amplification
+    illc = amp > 1e3
+    if illc.any():
+        noise_fast = np.median(rel_fast[illc] / amp[illc]); noise_strict = np.median(rel_strict[illc] / amp[illc])
+        print("ill-conditioned bins %d: median rel / amplification  fast %.3g  strict %.3g" % (illc.sum(), noise_fast, noise_strict))
+        assert noise_fast < 64 * np.finfo(float).eps and noise_strict < 64 * np.finfo(float).eps
+
+
+def test_strict_variant_two_plus_one_d_and_errors(fx):
+    from oracle import cf_oracle as cfo
+    cells = synthetic.columns_to_cells(synthetic.surface_vh(40, synthetic.SEEDS["cfg2"], three_d=False, viscous=True), 1)
+    sp = tables.species(fx, 1, "chosen_pikp"); g = tables.grid(fx); tab = tables.df_tables(fx, 1)
+    fl = tables.flags(df_mode=2, dimension=2)
+    ref, _, _ = cfo.smooth(fl, cells, sp, g, tab, None)
+    dN, _ = api.smooth_spectra(fl, cells, sp, g, tab, None, tile_variant=99)
+    rep = compare(dN, ref, tol=1e-12)
+    assert rep["ok"], rep
+    with pytest.raises(api.Is3dError):
+        api.smooth_spectra(tables.flags(df_mode=3, dimension=3), cells, sp, g, tab, tables.laguerre(fx), tile_variant=99)
+    with pytest.raises(api.Is3dError):
+        api.smooth_spectra(fl, cells, sp, g, tab, None, tile_variant=50)
+
+
 def test_two_plus_one_d_against_oracle(fx):
     from oracle import cf_oracle as cfo
     cells = synthetic.columns_to_cells(synthetic.surface_vh(300, synthetic.SEEDS["cfg2"], three_d=False, viscous=False), 1)
