@@ -855,20 +855,18 @@ extern "C" int is3d_b200_resonance_decays(const is3d_particle_list *pdg, int32_t
   if (opt_in) opt = *opt_in;
   cudaStream_t st = (cudaStream_t)opt.stream;
   const int64_t n_bins = (int64_t)n_chosen * gr->n_pT * gr->n_phi * gr->n_y;
-  double *dev = dN;
+  // the feed-down works on a scratch copy: an error (the reference exits there) leaves the caller's array untouched
   cudaEvent_t *ev = ws.ev;
   CU_CHECK(cudaEventRecord(ev[0], st));
-  if (opt.memory == 0) {
-    CU_CHECK(ws.dN.reserve((size_t)n_bins * 8 + 256));
-    dev = ws.dN.as<double>();
-    CU_CHECK(cudaMemcpyAsync(dev, dN, (size_t)n_bins * 8, cudaMemcpyHostToDevice, st));
-  }
+  CU_CHECK(ws.dN.reserve((size_t)n_bins * 8 + 256));
+  double *dev = ws.dN.as<double>();
+  CU_CHECK(cudaMemcpyAsync(dev, dN, (size_t)n_bins * 8, opt.memory == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
   CU_CHECK(cudaEventRecord(ev[1], st));
   int launches = 0; std::string err;
   const int rc = resonance_decays_device(pdg, n_chosen, chosen, gr, dimension, dev, st, &launches, &err);
   if (rc != IS3D_OK) { cudaStreamSynchronize(st); return fail(rc, err.c_str()); }
   CU_CHECK(cudaEventRecord(ev[2], st));
-  if (opt.memory == 0) CU_CHECK(cudaMemcpyAsync(dN, dev, (size_t)n_bins * 8, cudaMemcpyDeviceToHost, st));
+  CU_CHECK(cudaMemcpyAsync(dN, dev, (size_t)n_bins * 8, opt.memory == 0 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
   CU_CHECK(cudaEventRecord(ev[3], st));
   CU_CHECK(cudaEventSynchronize(ev[3]));
   if (stats) {

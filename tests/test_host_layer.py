@@ -120,8 +120,9 @@ def test_missing_parameter_is_an_error(fx):
 
 
 def test_operation_dispatch_rules(fx):
-    """what the host layer accepts: operation 1 (spectra) and 0 (spacetime distributions, viscous hydro only); the sampler,
-    resonance decays (disabled inside the reference itself) and mode 2 + operation 0 are refused with IS3D_ERR_UNSUPPORTED"""
+    """what the host layer accepts: operation 1 (spectra, optionally with the resonance-decay feed-down) and 0 (spacetime
+    distributions, viscous hydro only); the sampler, decays outside operation 1 or without decay tables (SMASH box list) and
+    mode 2 + operation 0 are refused with IS3D_ERR_UNSUPPORTED"""
     lib = api.lib()
     lib.is3d_b200_host_error.restype = C.c_char_p
 
@@ -135,8 +136,11 @@ def test_operation_dispatch_rules(fx):
     assert rc_for(operation=0)[0] == 0
     rc, msg = rc_for(operation=2)
     assert rc == 2 and "sampler" in msg
-    rc, msg = rc_for(operation=1, do_resonance_decays=1)
+    assert rc_for(operation=1, do_resonance_decays=1)[0] == 0
+    rc, msg = rc_for(operation=0, do_resonance_decays=1)
     assert rc == 2 and "resonance" in msg
+    rc, msg = rc_for(operation=1, do_resonance_decays=1, hrg_eos=3)
+    assert rc == 2 and "decay tables" in msg
     rc, msg = rc_for(operation=0, mode=2)
     assert rc == 2 and "anisotropic" in msg
 
