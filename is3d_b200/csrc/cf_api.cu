@@ -61,6 +61,7 @@ struct Device {
   std::mutex mu;                   // one call at a time per device
   Workspace ws;
   int sm_count = 0;
+  int l2_bytes = 0;
   bool init = false;
 };
 static Device g_dev[kMaxDevices];
@@ -134,6 +135,7 @@ static int current_device(Device **out)
   std::lock_guard<std::mutex> lk(D.mu);
   if (!D.init) {
     CU_CHECK(cudaDeviceGetAttribute(&D.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    CU_CHECK(cudaDeviceGetAttribute(&D.l2_bytes, cudaDevAttrL2CacheSize, dev));
     if (!D.ws.events) {
       for (auto &e : D.ws.ev) CU_CHECK(cudaEventCreate(&e));
       D.ws.events = true;
@@ -353,10 +355,16 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   if (n_chunks <= 0) {
     const int64_t target_blocks = (int64_t)g_sm_count * 96;             // >= 16 waves at 6 blocks/SM: small tail
     n_chunks = (int)((target_blocks + n_bintiles - 1) / n_bintiles);
+    // the blocks of one chunk run together (the grid is chunk-major) and each record is read by every block with that y / phi
+    // tile: keep a chunk's records within a third of L2, or the blocks drift apart and re-read them from HBM
+    // (measured at 90 k cells = 199 MB per chunk: 519 GB of DRAM reads for 2.2 GB of records, profiles/r2_traffic.json)
+    const int64_t rec_per_cell = ((int64_t)L.n_ytiles * L.nst * L.rec_y + (int64_t)L.n_ptiles * L.npt * kRec + kScal) * 8;
+    const int64_t l2_target = std::max<int64_t>((int64_t)Dp->l2_bytes / 3, (int64_t)8 << 20);
+    const int64_t n_chunks_l2 = (n_cells * rec_per_cell + l2_target - 1) / l2_target;
+    if (!iq && n_chunks_l2 > n_chunks) n_chunks = (int)std::min<int64_t>(n_chunks_l2, 1 << 20);
     n_chunks_wanted = n_chunks;                                         // reported next to the capped value (is3d_stats)
-    const int64_t max_partial_bytes = (int64_t)2 << 30;                 // keep the partial buffer <= 2 GiB
+    const int64_t max_partial_bytes = (int64_t)4 << 30;                 // keep the partial buffer <= 4 GiB (8 GiB with the second feqmod set)
     int64_t cap = max_partial_bytes / (n_bins * 8 > 0 ? n_bins * 8 : 1);
-    if (feqmod) cap /= 2;
     if (cap < 1) cap = 1;
     if (n_chunks > cap) n_chunks = (int)cap;
   }

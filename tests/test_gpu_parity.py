@@ -200,9 +200,10 @@ def test_sampled_bins_against_oracle_at_full_species(big, fx):
 def test_ill_conditioned_bins_strict_variant(big, fx, df_mode):
     """tile_variant 99 evaluates every term in the reference's own operation order (cf_strict.cu: no hoisting, no factorisation,
     cosh / sinh / exp / divisions per evaluation, -fmad=false); all that separates it from the oracle is the device libm (<= 2 ulp).
-    In the well-conditioned bins it therefore sits at ~1e-15 from the oracle -- and in the handful of bins where the restructured
-    kernel exceeds 1e-10 it moves by 1e-11 or more as well: those bins are uncertain in the reference's own arithmetic, which
-    is what the conditioning allowance of common.compare encodes."""
+    It meets the plain 1e-10 bar in EVERY bin, including the handful where the restructured kernel does not (measured: it
+    reproduces those bins exactly) -- so the deviation of the restructured kernel there is purely the different operation
+    order acting on a sum that cancels by a factor ~5e6 (|error| / amplification ~ 1 ulp), which is what the conditioning
+    allowance of common.compare encodes."""
     from oracle import cf_oracle as cfo
     cells, dev, sp, g, tab = big
     sub = {k: v[:64] for k, v in cells.items()}
@@ -225,11 +226,12 @@ def test_ill_conditioned_bins_strict_variant(big, fx, df_mode):
     print("bins where the restructured kernel exceeds 1e-10: %d" % bad.size)
     for b in bad:
         print("  amplification %.3g  fast %.3g  strict %.3g" % (amp[b], rel_fast[b], rel_strict[b]))
+    print("strict variant: max rel over all bins %.3g" % rel_strict.max())
     if bad.size:
         assert np.all(amp[bad] > 1e3)
-        # the reference-order evaluation moves in the same bins: at least 1e4 x its own well-conditioned deviation
-        assert np.median(rel_strict[bad]) > 1e4 * np.median(rel_strict[well][rel_strict[well] > 0]), (rel_strict[bad], np.median(rel_strict[well]))
-    # and the two evaluations are each other's peers in the ill-conditioned bins: same order of magnitude of noise per unit of amplification
+        assert np.all(rel_strict[bad] < REL_TOL)                      # the reference order meets the plain bar in exactly those bins
+        assert np.all(rel_fast[bad] / amp[bad] < 8 * np.finfo(float).eps)          # ~1 ulp of the cancelling terms
+    # per unit of amplification both evaluations stay within a few ulp in the ill-conditioned bins
     illc = amp > 1e3
     if illc.any():
         noise_fast = np.median(rel_fast[illc] / amp[illc]); noise_strict = np.median(rel_strict[illc] / amp[illc])
