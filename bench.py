@@ -200,7 +200,12 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------ roofline helpers
 # FP64-pipe instructions executed per evaluation (warp instructions per warp-evaluation, dead evaluations included), from the
 # committed ncu captures of the default kernel of each model (profiles/README.md names the file behind every number)
-FP64_INSTR_PER_EVAL = {1: 17.76, 2: None, 3: 22.6, 4: 22.6, 5: None, "ideal2d": None}
+FP64_INSTR_PER_EVAL = {1: 17.78,          # profiles/r2_ncu_full_lin14_200k_1chunk.json
+                       2: 20.12,          # profiles/r2_instr_cfg4ce.csv (smsp__inst_executed_pipe_fp64.sum x 32 / evaluations)
+                       3: 22.6,           # profiles/r1_ncu_full_cf_kernel_feqmod.json (Mike)
+                       4: 22.69,          # profiles/r2_ncu_full_cfg4jonah.json
+                       5: 27.24,          # profiles/r2_ncu_full_cfg5_vah.json
+                       "ideal2d": 10.57}  # profiles/r2_ncu_full_cfg2_ideal2d.json
 
 
 def alive_fraction(cells, sp, g, dim, n_sample=256, vah=False):
@@ -501,11 +506,15 @@ def main():
                 "traffic": None, "flops_per_evaluation": W, "kernel_ms": kernel_mean, "kernel_share_of_step": kernel_mean / ms_step,
                 "peak_source": "measured live: dependency-free DFMA chains on all SMs, %.1f s sustained (burst %.2f TFLOP/s); "
                                "MEASURED_PEAKS.json has no FP64 entry" % (2.0, peak_burst),
-                "hbm": {"record_bytes_per_launch": int(rec_bytes), "note": "records are re-read by every bin-tile column from L2/HBM; "
-                        "ncu capture of a 20 000-cell launch (profiles/r1_ncu_full_cf_kernel_lin14_v3.json): 67 MB DRAM read + 273 MB written "
-                        "in 169 ms = 2 GB/s, i.e. the path is not HBM-bound", "hbm_peak_gbs": _measured_hbm()},
-                "reading": "W is the reference's flop count per evaluation as written (SURVEY 8d); the restructured kernel executes ~18 FP64 "
-                           "instructions per evaluation, so frac can exceed 1 -- the FP64 pipe itself is 56 % busy in the ncu capture"}
+                "hbm": {"record_bytes_per_launch": int(rec_bytes), "note": "algorithmic bytes = the record arrays read once + one partial "
+                        "spectra array written per cell chunk; chunks are sized to a third of L2 so that the blocks sharing a chunk re-read it "
+                        "from L2 (ncu at 1 M cells: 6.2 GB DRAM read + 2.3 GB written per 8.3 s launch = 1 GB/s; with 199 MB chunks the same "
+                        "launch read 519 GB, profiles/r2_traffic.json): the path is not HBM-bound", "hbm_peak_gbs": _measured_hbm()},
+                "reading": "W is the reference's flop count per evaluation as written (SURVEY 8d); the restructured kernel executes fewer "
+                           "FP64 instructions per evaluation (fp64_instr_per_eval), so frac can exceed 1; pipe_frac is the hardware utilisation. "
+                           "Issue-slot reading (profiles/r2_ubench_mix_issue.txt): on B200 a warp-wide DFMA holds the scheduler ~2 cycles and an "
+                           "interleaved integer instruction ~1.7 more -- they do not overlap -- so the kernel time tracks the TOTAL warp "
+                           "instruction count (~38 per warp-evaluation at ~1.7 cycles each), not the FP64 share"}
 
     # hardware-side reading: FP64-pipe instructions actually executed per evaluation (ncu), the share of evaluations that are not
     # identically zero in the reference, and the resulting pipe utilisation (a warp-wide FP64 instruction holds the pipe 2 cycles)

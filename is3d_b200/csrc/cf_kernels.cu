@@ -265,6 +265,24 @@ cf_kernel(const HotParams hp)
           if (SB == 3) exp_neg_poly(-q[k], fq[k], fm[k]);
         }
       }
+      // SB >= 5 (linear models, 3+1D): shifted factorisation of the exponential.  With qm = max_k q[k] and d[k] = qm - q[k] >= 0,
+      //   e^{-x_jk} = e^{-(a_j - qm)} e^{-d[k]}:  one exponential per slot (of the group's SMALLEST argument xm_j = a_j - qm) and
+      // one per phi point and cell, a DMUL per evaluation.  Both factors lie in (0, 1], so -- unlike e^{-a_j} e^{+q_k} -- neither
+      // can overflow or underflow before the product does: whenever xm_j + max d < 707.7 both factors and the product are normal
+      // numbers; every other slot takes the per-member path below, which is the SB == 1 evaluation.  The group's aliveness and
+      // diluteness follow from xm_j alone.
+      double sd[NPT], eB[NPT]; int rare_hi = 0;
+      if (SB >= 5 && MODEL != M_FEQMOD && MODEL != M_VAH) {
+        double qm = q[0], qn = q[0];
+#pragma unroll
+        for (int k = 1; k < NPT; k++) { qm = fmax(qm, q[k]); qn = fmin(qn, q[k]); }
+#pragma unroll
+        for (int k = 0; k < NPT; k++) { sd[k] = qm - q[k]; double pp; int nn; exp_neg_poly(sd[k], pp, nn); eB[k] = exp_neg_fast(pp, nn); }
+        // slot j is "rare" when xm_j >= 707.7 - (qm - qn); compared on the high words (negative threshold: always)
+        rare_hi = __double2hiint(kRareX - (qm - qn));
+#pragma unroll
+        for (int k = 0; k < NPT; k++) q[k] = qm;         // q[] is not needed any more; keep one live value
+      }
       // delta-f polynomial without its (u.p)^2 part, linear models: mT^2 Qyy + pT^2 Qpp + (..) m^2 + mT pT (R2 U2 - R1 U1)
       auto sterm = [&](int j, int k, double h0, double h1, double h2) -> double {
         if (PAIR) return fma(mTpT, pair_tab[(c * NYT + j) * NPT + k], h0 + g0[k]);
