@@ -24,6 +24,7 @@ SOURCES = [
     ("cf_prepare.cu", ["-fmad=false"]),
     ("cf_decays.cu", ["-fmad=false"]),
     ("cf_strict.cu", ["-fmad=false"]),
+    ("cf_shift.cu", []),
     ("cf_api.cu", []),
     ("host_math.cpp", []),
     ("host_io.cpp", []),

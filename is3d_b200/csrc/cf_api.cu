@@ -285,7 +285,9 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   if (iq && vah) return fail(IS3D_ERR_UNSUPPORTED, "spacetime distributions exist for mode 1 surfaces only");
   if (iq && iq->mode == 2 && !dim2) return fail(IS3D_ERR_ARGUMENT, "per-slot integration is a 2+1D pass");
   if (iq && (!iq->pT_weight || !iq->phi_weight)) return fail(IS3D_ERR_ARGUMENT, "pT / phi quadrature weights missing");
-  // tile_variant: 0 = model default (tuned on B200, see profiles/), k > 0 = table entry k - 1 (tuning / tests)
+  // tile_variant: 0 = model default (tuned on B200, see profiles/), k > 0 = table entry k - 1 (tuning / tests).
+  // Defaults: linear-df models (and ideal f_eq) on 3+1D tiles with <= 64 pT points run cf_shift_kernel (tile_variant 23);
+  // modified equilibrium, the anisotropic model, 2+1D and operation = 0 run cf_kernel.
   // 17..21 = shapes of the factored kernel (cf_factored.cu; linear-df models on 3+1D tiles, >= 16 species): opt-in for the main
   // pass (measured within +-10 % of cf_kernel on B200), always used for the sparse linear-branch pass of
   // df_mode 3 / 4, where its per-cell skip of dead records makes that pass nearly free
@@ -293,17 +295,28 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   int variant, fvariant = -1;
   const bool f_ok = factored_supported(model, L) && !iq;      // operation = 0 integrates over the pT lanes of a block (cf_kernel)
   const bool strict = (opt.tile_variant == kStrictVariant);
+  // 22..25 = shapes of the shifted-factor kernel (cf_shift.cu; linear-df models on 3+1D tiles, <= 64 pT points)
+  int svariant = -1;
+  const int first_shift = kNumVariants + kNumFactoredVariants + 1;
+  const bool s_ok = shift_supported(model, L) && !iq;
   if (strict && (iq || vah || feqmod)) return fail(IS3D_ERR_ARGUMENT, "tile_variant 99 (strict diagnostic kernel) needs df_mode 1/2, mode 1 and operation 1");
-  if (opt.tile_variant < 0 || (opt.tile_variant > kNumVariants + kNumFactoredVariants && !strict)) return fail(IS3D_ERR_ARGUMENT, "unknown tile_variant");
+  if (opt.tile_variant < 0 || (opt.tile_variant >= first_shift + kNumShiftVariants && !strict)) return fail(IS3D_ERR_ARGUMENT, "unknown tile_variant");
+  if (opt.tile_variant >= first_shift && !strict) {
+    if (!s_ok) return fail(IS3D_ERR_ARGUMENT, "tile_variant 22..25 (shifted-factor kernel) needs df_mode 1/2, dimension 3, operation 1 and <= 64 pT points");
+    svariant = opt.tile_variant - first_shift;
+  }
   if (opt.tile_variant >= 1 && opt.tile_variant <= kNumVariants) variant = opt.tile_variant - 1;
   else if (opt.tile_variant > kNumVariants && opt.tile_variant <= kNumVariants + kNumFactoredVariants) {
     if (!f_ok) return fail(IS3D_ERR_ARGUMENT, "tile_variant 17..21 (factored kernel) needs df_mode 1/2, dimension 3, operation 1 and >= 16 species");
     variant = opt.tile_variant - 1; fvariant = variant - kNumVariants;
   }
+  else if (svariant >= 0) variant = opt.tile_variant - 1;
   else if (sum_slots) variant = (model == M_FEQMOD || model == M_VAH) ? 12 : (model == M_IDEAL ? 13 : 10);
+  else if (s_ok) { svariant = 1; variant = first_shift - 1 + svariant; }   // linear-df models, 3+1D: cf_shift_kernel<7, 3, 3 blocks/SM>, +15..20 % over cf_kernel
   else variant = (model == M_VAH || model == M_FEQMOD) ? 11 : 9;
   int nyt, npt, ct, max_warps;
   if (fvariant >= 0) factored_variant_shape(fvariant, &nyt, &npt, &ct, &max_warps);
+  else if (svariant >= 0) shift_variant_shape(svariant, &nyt, &npt, &ct, &max_warps);
   else hot_variant_shape(variant, sum_slots ? 1 : 0, &nyt, &npt, &ct, &max_warps);
   L.nst = sum_slots ? L.n_slots : nyt;
   L.n_ytiles = sum_slots ? 1 : (L.n_slots + nyt - 1) / nyt;
@@ -347,6 +360,7 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
       if (launched < best) { best = launched; n_warps = w; }
     }
   }
+  if (svariant >= 0) n_warps = 4;                           // cf_shift_kernel blocks are always 4 warps
   int n_groupblocks = (n_groups + n_warps - 1) / n_warps;
   if (fvariant >= 0) factored_blocking(sp->n, gr->n_pT, L.n_ptiles, &n_warps, &n_groupblocks);   // lanes = species, warps = phi tiles
   const int64_t n_bintiles = (int64_t)n_groupblocks * L.n_ytiles * (fvariant >= 0 ? 1 : L.n_ptiles);      // blocks per cell chunk
@@ -567,6 +581,9 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   hp.one_hi = 0x3ff00000;
   hp.reg_lo = fl->regulate_deltaf ? 0 : (int)0x80000000; hp.reg_hi = fl->regulate_deltaf ? 0x40000000 : 0x7fffffff;
   hp.reg_chk = fl->regulate_deltaf ? 0x3fffffffu : 0xffffffffu;
+  { const double ec[8] = {-369.3299304675746, 6755399441055744.0, -0.00270760617331689, -7.453964567463233e-13,      // = kExpR, kExpC (cf_device.cuh)
+                          4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 0.0};
+    for (int i = 0; i < 8; i++) hp.ec[i] = ec[i]; }
   hp.outflow_thr = (fl->outflow && !vah) ? 0LL : (long long)0x8000000000000000ULL;   // the anisotropic kernel has no Theta(p.dsigma)
   const double hbarC = 0.197327053;
   hp.pT_max = *std::max_element(gr->pT, gr->pT + gr->n_pT);
@@ -578,6 +595,7 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   }
   if (strict) {}                                              // the bins were summed by launch_strict above
   else if (fvariant >= 0) CU_CHECK(launch_factored(model, hp, fvariant, st, nullptr));
+  else if (svariant >= 0) CU_CHECK(launch_shift(model, hp, svariant, st, nullptr));
   else CU_CHECK(launch_hot(model, hp, variant, st, nullptr));
   if (!strict) stt.gpu_launches++;
   int reduce_sets = 1;

@@ -10,6 +10,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "cf_internal.h"
 
 namespace is3d {
 
@@ -249,6 +250,53 @@ __device__ __forceinline__ double clamp_unit(double v, int thr_hi, int one_hi)
   const int hi2 = big ? ((hi & 0x80000000) | one_hi) : hi;
   const int lo2 = big ? 0 : __double2loint(v);
   return __hiloint2double(hi2, lo2);
+}
+
+// Bose/Fermi factor 1 / (e^x + Theta) from a = e^{-x}
+__device__ __forceinline__ double occupation(double a, double sign) { return a * rcp_fast(fma(sign, a, 1.0)); }
+// The same plus 1 - Theta f_eq, which equals 1 / (1 + Theta e^{-x}) exactly: the reciprocal itself (one DFMA less, and more
+// accurate than the reference's 1 - sign * feq where that cancels)
+__device__ __forceinline__ double occupation_bar(double a, double sign, double &feqbar)
+{ feqbar = rcp_fast(fma(sign, a, 1.0)); return a * feqbar; }
+// dilute form, a < 2^-18: 1 / (1 + Theta a) = 1 - Theta a + a^2 - ... truncated after a^2 (|error| < a^3 < 5.2e-17)
+__device__ __forceinline__ double occupation_bar_dilute(double a, double sign, double &feqbar)
+{ feqbar = fma(a, a, fma(-sign, a, 1.0)); return a * feqbar; }
+
+// f_eq (1 + df) of the linear-df models (x = u.p/T, s = partial delta-f polynomial, see cf_prepare.cu) for a group of N evaluations, staged so that the N dependency chains can be interleaved
+template <int MODEL, int N>
+__device__ __forceinline__ void distribution_group(const double (&x)[N], bool maybe_rare, bool all_dilute, const double (&s)[N], double K2, double K3,
+                                                   double sign, int reg_thr, int one_hi, double (&f)[N])
+{
+  double p[N], a[N], dfs[N]; int n[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    exp_neg_poly(x[i], p[i], n[i]);
+    if (MODEL == M_IDEAL) dfs[i] = 0.0;
+    else if (MODEL == M_LIN14) dfs[i] = fma(K2 * x[i], x[i], s[i]);
+    else dfs[i] = fma(s[i], rcp_fast(x[i]), K2 * x[i]);
+  }
+  if (__builtin_expect(maybe_rare, 0)) {              // both sides define a[]: no register shuffling on the fast side
+#pragma unroll
+    for (int i = 0; i < N; i++) a[i] = exp_neg_slow(x[i], p[i], n[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i++) a[i] = exp_neg_fast(p[i], n[i]);
+  }
+  double feq[N], feqbar[N];
+  if (all_dilute) {                                    // warp-divergent only where light species meet central rapidities
+#pragma unroll
+    for (int i = 0; i < N; i++) feq[i] = occupation_bar_dilute(a[i], sign, feqbar[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i++) feq[i] = occupation_bar(a[i], sign, feqbar[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    if (MODEL == M_IDEAL) { f[i] = feq[i]; continue; }
+    double df = (MODEL == M_JONAHLIN) ? fma(feqbar[i], dfs[i], K3) : feqbar[i] * dfs[i];
+    df = clamp_unit(df, reg_thr, one_hi);
+    f[i] = fma(feq[i], df, feq[i]);
+  }
 }
 
 }  // namespace is3d

@@ -78,6 +78,8 @@ struct HotParams {
   int regulate_thr;                                // high-word threshold of |df| >= 1, see clamp_unit()
   int reg_lo, reg_hi;                              // factored kernel: bounds of the high word of g = 1 + df (0, 0x40000000 | INT_MIN, INT_MAX)
   unsigned reg_chk;                                // ... and the unsigned high word above which a member needs the clamp
+  double ec[8];                                    // cf_shift.cu: constants of exp_neg_poly (kExpR[0..3], kExpC[0..2]) as kernel-parameter
+                                                   // operands: c[0x0][..] feeds a DFMA directly, no register and no LDC
   int one_hi;                                      // 0x3ff00000 (high word of 1.0) as a run-time value, see clamp_unit()
   // operation = 0 (spacetime distributions): momentum-integrated epilogue instead of the spectra bins
   int integ_mode;                                  // 0 spectra; 1 sum over (slot, phi, pT) per chunk; 2 per slot, sum over (phi, pT)
@@ -125,6 +127,11 @@ constexpr int kFactoredMinSpecies = 16;      // its lanes are species: shorter l
 // warps = phi tiles of a block; n_groupblocks = blocks per (cell chunk, y tile) = species groups x pT points x phi blocks
 void factored_blocking(int n_species, int n_pT, int n_ptiles, int *n_warps, int *n_groupblocks);
 cudaError_t launch_factored(int model, const HotParams &hp, int fvariant, cudaStream_t st, size_t *smem_out);
+// shifted-factor kernel (cf_shift.cu): linear-df models, 3+1D tiles, <= 64 pT points; same lanes and grid as cf_kernel, 4-warp blocks
+constexpr int kNumShiftVariants = 4;         // tile_variant 22..25
+bool shift_supported(int model, const Layout &L);
+void shift_variant_shape(int v, int *nyt, int *npt, int *ct, int *max_warps);
+cudaError_t launch_shift(int model, const HotParams &hp, int v, cudaStream_t st, size_t *smem_out);
 // slot records of padding / skipped cells carry this A = u.p / (mT T): every evaluation is dead (exp overflows, f = 0 exactly)
 constexpr double kDeadSlotA = 1.0e6;
 

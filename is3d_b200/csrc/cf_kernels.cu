@@ -22,16 +22,6 @@
 
 namespace is3d {
 
-// Bose/Fermi factor 1 / (e^x + Theta) from a = e^{-x}
-__device__ __forceinline__ double occupation(double a, double sign) { return a * rcp_fast(fma(sign, a, 1.0)); }
-// The same plus 1 - Theta f_eq, which equals 1 / (1 + Theta e^{-x}) exactly: the reciprocal itself (one DFMA less, and more
-// accurate than the reference's 1 - sign * feq where that cancels)
-__device__ __forceinline__ double occupation_bar(double a, double sign, double &feqbar)
-{ feqbar = rcp_fast(fma(sign, a, 1.0)); return a * feqbar; }
-// dilute form, a < 2^-18: 1 / (1 + Theta a) = 1 - Theta a + a^2 - ... truncated after a^2 (|error| < a^3 < 5.2e-17)
-__device__ __forceinline__ double occupation_bar_dilute(double a, double sign, double &feqbar)
-{ feqbar = fma(a, a, fma(-sign, a, 1.0)); return a * feqbar; }
-
 // f_eq (1 + df) of the linear-df models; x = u.p/T, s = partial delta-f polynomial (see cf_prepare.cu)
 template <int MODEL>
 __device__ __forceinline__ double distribution(double x, double s, double K2, double K3, double sign, int reg_thr, int one_hi)
@@ -87,28 +77,20 @@ __device__ __forceinline__ double distribution_from_a(double a, double x, double
   return fma(feq, df, feq);
 }
 
-// Same as distribution() for a group of N evaluations, staged so that the N dependency chains can be interleaved
+// The same stages for a group whose a[i] = e^{-x[i]} are already known (shifted-factor exponential, SB >= 5): the dilute / full
+// occupation branch wraps the whole group, so that it stays a branch (a per-member `if` gets if-converted: both sides executed)
 template <int MODEL, int N>
-__device__ __forceinline__ void distribution_group(const double (&x)[N], bool maybe_rare, bool all_dilute, const double (&s)[N], double K2, double K3,
-                                                   double sign, int reg_thr, int one_hi, double (&f)[N])
+__device__ __forceinline__ void distribution_group_from_a(const double (&a)[N], const double (&x)[N], bool all_dilute, const double (&s)[N], double K2,
+                                                          double K3, double sign, int reg_thr, int one_hi, double (&f)[N])
 {
-  double p[N], a[N], dfs[N]; int n[N];
+  double dfs[N], feq[N], feqbar[N];
 #pragma unroll
   for (int i = 0; i < N; i++) {
-    exp_neg_poly(x[i], p[i], n[i]);
     if (MODEL == M_IDEAL) dfs[i] = 0.0;
     else if (MODEL == M_LIN14) dfs[i] = fma(K2 * x[i], x[i], s[i]);
     else dfs[i] = fma(s[i], rcp_fast(x[i]), K2 * x[i]);
   }
-  if (__builtin_expect(maybe_rare, 0)) {              // both sides define a[]: no register shuffling on the fast side
-#pragma unroll
-    for (int i = 0; i < N; i++) a[i] = exp_neg_slow(x[i], p[i], n[i]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < N; i++) a[i] = exp_neg_fast(p[i], n[i]);
-  }
-  double feq[N], feqbar[N];
-  if (all_dilute) {                                    // warp-divergent only where light species meet central rapidities
+  if (all_dilute) {
 #pragma unroll
     for (int i = 0; i < N; i++) feq[i] = occupation_bar_dilute(a[i], sign, feqbar[i]);
   } else {
@@ -279,7 +261,7 @@ cf_kernel(const HotParams hp)
 #pragma unroll
         for (int k = 0; k < NPT; k++) { sd[k] = qm - q[k]; double pp; int nn; exp_neg_poly(sd[k], pp, nn); eB[k] = exp_neg_fast(pp, nn); }
         // slot j is "rare" when xm_j >= 707.7 - (qm - qn); compared on the high words (negative threshold: always)
-        rare_hi = __double2hiint(kRareX - (qm - qn));
+        rare_hi = __double2hiint(__hiloint2double(kRareHi, 0) - (qm - qn));
 #pragma unroll
         for (int k = 0; k < NPT; k++) q[k] = qm;         // q[] is not needed any more; keep one live value
       }
@@ -404,6 +386,33 @@ cf_kernel(const HotParams hp)
                 const double f = distribution<MODEL>(x, s, K2, K3, sign, reg_thr, one_hi);
                 accumulate_outflow(accj[k], pds, f, thr);
               }
+            }
+          } else if (SB >= 5) {
+            // shifted factorisation (see the per-cell hoists above): q[0] holds qm, sd[k] = qm - q_k, eB[k] = e^{-sd[k]}
+            const double xm = a - q[0];                                     // smallest argument of the group
+            const int xh = __double2hiint(xm);
+            if (xh <= kAliveHi) {
+              double xs[NPT], sv[NPT], pv[NPT];
+#pragma unroll
+              for (int k = 0; k < NPT; k++) {
+                xs[k] = xm + sd[k];
+                pv[k] = fma(w, pd[k], cpm);
+                sv[k] = sterm(j, k, h0, h1, h2);
+              }
+              double fv[NPT];
+              if (__builtin_expect(xh >= rare_hi, 0)) {                       // some member may be sub-normal or dead: per-member path
+                distribution_group<MODEL, NPT>(xs, true, false, sv, K2, K3, sign, reg_thr, one_hi, fv);
+              } else {
+                double pe, av[NPT]; int ne;
+                exp_neg_poly(xm, pe, ne);
+                const double eA = exp_neg_fast(pe, ne);
+#pragma unroll
+                for (int k = 0; k < NPT; k++) av[k] = eA * eB[k];
+                // a_k <= e^{-xm} < 2^-18 for every member once xm >= 12.5
+                distribution_group_from_a<MODEL, NPT>(av, xs, xh >= kDiluteHi, sv, K2, K3, sign, reg_thr, one_hi, fv);
+              }
+#pragma unroll
+              for (int k = 0; k < NPT; k++) accumulate_pos(accj[k], pv[k], fv[k], thr_hi);
             }
           } else if (SB == 3) {
             // e^{-x} = e^{-mT Ax} e^{+pT Bx}: one exponential per slot and one per phi point instead of one per evaluation
@@ -573,7 +582,7 @@ cudaError_t launch_reduce(const double *partial, int n_chunks, int64_t n_bins, i
 struct Shape { int nyt, npt, ct, minb, sb; };
 static const Shape kShapes3D[] = {
   {7, 3, 8, 7, 4}, {7, 3, 8, 7, 1}, {7, 3, 16, 5, 4}, {7, 4, 16, 3, 4}, {7, 2, 16, 6, 4}, {3, 6, 16, 3, 0}, {7, 6, 16, 2, 4}, {7, 3, 16, 4, 0},
-  {7, 3, 16, 4, 3}, {7, 3, 16, 3, 4}, {7, 3, 16, 3, 3}, {7, 3, 16, 4, 1}, {7, 3, 16, 3, 1}, {7, 4, 16, 4, 1}, {7, 2, 16, 6, 1}, {7, 3, 16, 4, 4}};
+  {7, 3, 16, 4, 3}, {7, 3, 16, 3, 4}, {7, 3, 16, 3, 3}, {7, 3, 16, 4, 1}, {7, 3, 16, 3, 5}, {7, 4, 16, 3, 5}, {7, 2, 16, 6, 1}, {7, 3, 16, 4, 5}};
 static const Shape kShapes2D[] = {
   {1, 3, 1, 4, 0}, {1, 4, 1, 4, 0}, {1, 6, 1, 3, 0}, {1, 8, 1, 3, 0}, {1, 2, 1, 5, 0}, {1, 12, 1, 2, 0}, {1, 4, 1, 3, 0}, {1, 1, 1, 6, 0},
   {1, 6, 1, 3, 3}, {1, 3, 1, 4, 1}, {1, 4, 1, 4, 3}, {1, 4, 1, 3, 1}, {1, 6, 1, 3, 1}, {1, 8, 1, 3, 3}, {1, 3, 1, 5, 1}, {1, 12, 1, 2, 3}};
@@ -652,10 +661,10 @@ static cudaError_t launch_model(const HotParams &hp, int variant, cudaStream_t s
       case 9: return launch_one<MODEL, 7, 3, false, 3, 4>(hp, st, smem_out);
       case 10: return launch_one<MODEL, 7, 3, false, 3, 3>(hp, st, smem_out);
       case 11: return launch_one<MODEL, 7, 3, false, 4, 1>(hp, st, smem_out);
-      case 12: return launch_one<MODEL, 7, 3, false, 3, 1>(hp, st, smem_out);
-      case 13: return launch_one<MODEL, 7, 4, false, 4, 1>(hp, st, smem_out);
+      case 12: return launch_one<MODEL, 7, 3, false, 3, 5>(hp, st, smem_out);
+      case 13: return launch_one<MODEL, 7, 4, false, 3, 5>(hp, st, smem_out);
       case 14: return launch_one<MODEL, 7, 2, false, 6, 1>(hp, st, smem_out);
-      case 15: return launch_one<MODEL, 7, 3, false, 4, 4>(hp, st, smem_out);
+      case 15: return launch_one<MODEL, 7, 3, false, 4, 5>(hp, st, smem_out);
       default: break;
     }
   }

@@ -507,12 +507,14 @@ def test_factored_variants_against_oracle(fx, case):
     ref, _, _ = cfo.smooth(fl, cells, sp, g, tab, None, conditioning=cond)
     for variant in (0, 17, 18, 19, 20, 21):
         dN, st = api.smooth_spectra(fl, cells, sp, g, tab, None, tile_variant=variant)
-        assert st["tile_variant"] == (9 if variant == 0 else variant - 1)
+        assert st["tile_variant"] == (22 if variant == 0 else variant - 1)        # default: cf_shift_kernel 7 x 3
         rep = compare(dN, ref, conditioning=cond)
         assert rep["ok"], (case, variant, rep, compare(dN, ref))
-    # and the (species, pT)-lane kernel on the same problem
-    dN, st = api.smooth_spectra(fl, cells, sp, g, tab, None, tile_variant=10)
-    assert compare(dN, ref, conditioning=cond)["ok"]
+    # and the (species, pT)-lane kernels on the same problem: staged groups (10), the shifted-factor exponential inside cf_kernel
+    # (13, 14, 16) and the shifted-factor kernel cf_shift.cu (22..25)
+    for variant in (10, 13, 14, 16, 22, 23, 24, 25):
+        dN, st = api.smooth_spectra(fl, cells, sp, g, tab, None, tile_variant=variant)
+        assert compare(dN, ref, conditioning=cond)["ok"], (case, variant)
 
 
 def test_factored_ragged_grids_and_chunks(fx):

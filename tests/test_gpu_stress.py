@@ -42,8 +42,9 @@ def test_stress_surface(fx, name, df_mode):
         fl = tables.flags(df_mode=df_mode, dimension=3, **extra)
         cond = np.zeros(5 * 32 * 24 * 21) if df_mode in (1, 2) else None
         ref, skipped, breakdown = cfo.smooth(fl, cells, sp, g, tab, gla, conditioning=cond)
-        got, st = api.smooth_spectra(fl, cells, sp, g, tab, gla)
-        rep = compare(got, ref, conditioning=cond)
-        assert rep["ok"], (extra, rep)
-        assert st["cells_feqmod_breakdown"] == breakdown and st["cells_skipped_udsigma"] == skipped
-        assert np.isfinite(got).all()
+        for variant in ((0, 13, 16, 22, 24, 25) if df_mode in (1, 2) else (0,)):  # default and the shifted-factor exponential (cf_kernel SB 5, cf_shift.cu)
+            got, st = api.smooth_spectra(fl, cells, sp, g, tab, gla, tile_variant=variant)
+            rep = compare(got, ref, conditioning=cond)
+            assert rep["ok"], (extra, variant, rep)
+            assert st["cells_feqmod_breakdown"] == breakdown and st["cells_skipped_udsigma"] == skipped
+            assert np.isfinite(got).all()
