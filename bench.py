@@ -200,8 +200,8 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------ roofline helpers
 # FP64-pipe instructions executed per evaluation (warp instructions per warp-evaluation, dead evaluations included), from the
 # committed ncu captures of the default kernel of each model (profiles/README.md names the file behind every number)
-FP64_INSTR_PER_EVAL = {1: 17.78,          # profiles/r2_ncu_full_lin14_200k_1chunk.json
-                       2: 20.12,          # profiles/r2_instr_cfg4ce.csv (smsp__inst_executed_pipe_fp64.sum x 32 / evaluations)
+FP64_INSTR_PER_EVAL = {1: 13.75,          # profiles/r2_ncu_full_shift_default.json (cf_shift_kernel; cf_kernel: 17.78, r2_ncu_full_lin14_200k_1chunk.json)
+                       2: 16.11,          # profiles/r2_instr_cfg4ce_shift.csv (smsp__inst_executed_pipe_fp64.sum x 32 / evaluations; cf_kernel: 20.12)
                        3: 22.6,           # profiles/r1_ncu_full_cf_kernel_feqmod.json (Mike)
                        4: 22.69,          # profiles/r2_ncu_full_cfg4jonah.json
                        5: 27.24,          # profiles/r2_ncu_full_cfg5_vah.json
@@ -514,7 +514,7 @@ def main():
                            "FP64 instructions per evaluation (fp64_instr_per_eval), so frac can exceed 1; pipe_frac is the hardware utilisation. "
                            "Issue-slot reading (profiles/r2_ubench_mix_issue.txt): on B200 a warp-wide DFMA holds the scheduler ~2 cycles and an "
                            "interleaved integer instruction ~1.7 more -- they do not overlap -- so the kernel time tracks the TOTAL warp "
-                           "instruction count (~38 per warp-evaluation at ~1.7 cycles each), not the FP64 share"}
+                           "instruction count (30 per warp-evaluation in cf_shift_kernel, 38 in cf_kernel, at ~1.7-1.8 cycles each), not the FP64 share"}
 
     # hardware-side reading: FP64-pipe instructions actually executed per evaluation (ncu), the share of evaluations that are not
     # identically zero in the reference, and the resulting pipe utilisation (a warp-wide FP64 instruction holds the pipe 2 cycles)
