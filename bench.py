@@ -420,6 +420,16 @@ def main():
     sync_all()
     clocks = sampler.stop() if sampler else None
     ms_total = e0.elapsed_time(e1)
+    if sampler and world == 1 and clocks.get("sm_mhz") is None:
+        # the timed region is shorter than nvidia-smi's sampling period (cfg2: 57 ms per step): sample the clocks while the same
+        # steps repeat, untimed, for 1.5 s
+        sampler = ClockSampler(local)
+        t_rep = time.perf_counter()
+        while time.perf_counter() - t_rep < 1.5:
+            step_device()
+            torch.cuda.synchronize()
+        clocks = sampler.stop()
+        clocks["note"] = "sampled during an untimed 1.5 s repetition of the timed steps (timed region %.0f ms is shorter than the sampling period)" % ms_total
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
