@@ -193,7 +193,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "evaluations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 
@@ -308,11 +308,33 @@ def run_single_process(args):
         "multi_gpu_parity": {"cells": int(min(n_cells, 100_000)), "max_rel_err_vs_1gpu": float(np.max(np.abs(multi_small[nz] - single[nz]) / single[nz])),
                              "zero_pattern_equal": bool(np.array_equal(single == 0, multi_small == 0))},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 # ------------------------------------------------------------------------------------------------ our arm
+# stdout carries exactly ONE line, the JSON record: while the benchmark runs, file descriptor 1 points at stderr, so that
+# whatever libraries print there (NCCL's "NCCL version ..." banner when the box sets NCCL_DEBUG, the reference binary's progress
+# lines) cannot precede it
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -575,7 +597,7 @@ def main():
         "fraction_of_fp64_peak": achieved / peak_sustained, "multi_gpu_parity": multi_parity,
         "timing": {"prepare_ms": sum(prepare_ms) / len(prepare_ms), "kernel_ms": kernel_mean, "reduce_ms": sum(reduce_ms) / len(reduce_ms)},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
