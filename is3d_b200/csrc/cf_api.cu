@@ -367,7 +367,9 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
   int n_chunks = opt.n_chunks;
   int n_chunks_wanted = n_chunks;
   if (n_chunks <= 0) {
-    const int64_t target_blocks = (int64_t)g_sm_count * 96;             // >= 16 waves at 6 blocks/SM: small tail
+    // >= 64 waves at 3 blocks/SM: the last, partly filled wave costs < 1 % (a block lasts tens of ms, its fixed cost is us; at
+    // 96 blocks per SM the 125 k-cell shards of an 8-GPU run lost 1.5 % to the tail)
+    const int64_t target_blocks = (int64_t)g_sm_count * 192;
     n_chunks = (int)((target_blocks + n_bintiles - 1) / n_bintiles);
     // the blocks of one chunk run together (the grid is chunk-major) and each record is read by every block with that y / phi
     // tile: keep a chunk's records within a third of L2, or the blocks drift apart and re-read them from HBM
