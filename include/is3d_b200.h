@@ -91,9 +91,12 @@ typedef struct {
   int32_t memory;            /* 0: surface arrays and dN live in host memory; 1: they are device pointers on the current device */
   void *stream;              /* cudaStream_t to launch on (NULL = default stream) */
   int32_t n_chunks;          /* cell-range split used for load balance; 0 = choose */
-  int32_t tile_variant;      /* kernel register-tile variant: 0 = tuned default for the model, k = 1..16 selects table entry k - 1,
-                                17..21 = shapes of the factored kernel (df_mode 1/2, 3+1D, >= 16 species), 99 = strict diagnostic kernel
-                                (df_mode 1/2 in the reference's own operation order, one thread per bin: ~50x slower, tests only) */
+  int32_t tile_variant;      /* kernel variant: 0 = tuned default for the model (df_mode 1 / 2 and ideal f_eq on 3+1D tiles with <= 64 pT
+                                points: shifted-factor kernel 23; everything else: cf_kernel); 1..16 = register-tile table of cf_kernel;
+                                17..21 = shapes of the factored kernel (df_mode 1/2, 3+1D, >= 16 species); 22..25 = shapes of the
+                                shifted-factor kernel (df_mode 1/2, 3+1D, <= 64 pT points); 99 = strict diagnostic kernel (df_mode 1/2 in
+                                the reference's own operation order, one thread per bin: ~50x slower, tests only).  A variant that does
+                                not apply to the call returns IS3D_ERR_ARGUMENT. */
   int32_t reserved[4];
 } is3d_options;
 
@@ -106,7 +109,7 @@ typedef struct {
   int32_t n_chunks, tile_variant;
   int32_t n_gpus;                  /* devices that worked on this call (times above: slowest device) */
   double allreduce_ms;             /* multi-GPU: the NCCL all-reduce of the spectra array */
-  int32_t n_chunks_wanted;         /* chunks the load-balance rule asked for; > n_chunks when the 2 GiB partial-sum cap cut it down */
+  int32_t n_chunks_wanted;         /* chunks the load-balance rule asked for; > n_chunks when the 4 GiB cap on the partial-sum buffer cut it down */
   int32_t reserved;
 } is3d_stats;
 
