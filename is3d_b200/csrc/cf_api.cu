@@ -459,7 +459,7 @@ static int smooth_core(const is3d_flags *fl, const is3d_surface *sf, const is3d_
     {sf->dan, true, &rc.dan}, {sf->ux, true, &rc.ux}, {sf->uy, true, &rc.uy}, {sf->un, true, &rc.un},
     {sf->T, !vah, &rc.T}, {sf->P, !vah, &rc.P}, {sf->E, !vah, &rc.E},
     {sf->pixx, vah || sh, &rc.pixx}, {sf->pixy, vah || sh, &rc.pixy}, {sf->pixn, vah || sh, &rc.pixn}, {sf->piyy, vah || sh, &rc.piyy},
-    {sf->piyn, vah || sh, &rc.piyn}, {sf->bulkPi, vah ? bk : bk, &rc.bulkPi},
+    {sf->piyn, vah || sh, &rc.piyn}, {sf->bulkPi, bk, &rc.bulkPi},
     {sf->pitt, vah, &rc.pitt}, {sf->pitx, vah, &rc.pitx}, {sf->pity, vah, &rc.pity}, {sf->pitn, vah, &rc.pitn}, {sf->pinn, vah, &rc.pinn},
     {sf->Wx, vah, &rc.Wx}, {sf->Wy, vah, &rc.Wy}, {sf->Lambda, vah, &rc.Lambda}, {sf->aL, vah, &rc.aL},
     {sf->c0, vah, &rc.c0}, {sf->c1, vah, &rc.c1}, {sf->c2, vah, &rc.c2}, {sf->c3, vah, &rc.c3}, {sf->c4, vah, &rc.c4}};

@@ -29,11 +29,11 @@ namespace is3d {
 
 namespace {
 
-constexpr int kShiftMaxPT = 64;
-constexpr int kUltraHi = 0x4042C000;       // high word of 37.5: e^{-x} < 2^-54           // pT points the per-tile e^{-pT dB} table is laid out for
+constexpr int kShiftMaxPT = 64;           // pT points the per-tile e^{-pT dB} table is laid out for
+constexpr int kUltraHi = 0x4042C000;      // high word of 37.5: e^{-x} < 2^-54
 
 // g = 1 + df clamped to [0, 2] (regulate_deltaf, smooth_kernels.cpp:328) and zeroed where p.dsigma fails the outflow test (:285),
-// all on the integer pipe from the high words: 5 instructions (VIMNMX3, 2 ISETP, 2 SEL) for both features.
+// all on the integer pipe from the high words: 6 instructions (2 VIMNMX, 2 ISETP, 2 SEL) for both features.
 //   reg_lo / reg_hi / reg_chk = 0 / 0x40000000 / 0x3fffffff with regulation on (g keeps its low word iff its high word read as
 //   unsigned is <= reg_chk), INT_MIN / INT_MAX / 0xffffffff off;  thr_hi = 0 with outflow on, INT_MIN off.
 // A masked member contributes p.dsigma f_eq 0 = +-0 to the accumulator, i.e. nothing.
