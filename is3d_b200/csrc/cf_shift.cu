@@ -83,8 +83,9 @@ cf_shift_kernel(const HotParams hp)
   const int stage_doubles = y_doubles + p_doubles + s_doubles;
   double *stage_base = reinterpret_cast<double *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(stage_base + (size_t)kStages * stage_doubles);
-  double *pair_tab = reinterpret_cast<double *>(full + kStages);                 // [CT][NYT][NPT]
-  double *eb_tab = pair_tab + CT * NYT * NPT;                                    // [CT][NPT][n_pT]  e^{-pT (Bmax - B_k)}
+  constexpr int NPP = (NPT + 1) & ~1;                                            // pair-table row padded to whole 16-byte loads
+  double *pair_tab = reinterpret_cast<double *>(full + kStages);                 // [CT][NYT][NPP]
+  double *eb_tab = pair_tab + CT * NYT * NPP;                                    // [CT][NPT][n_pT]  e^{-pT (Bmax - B_k)}
   double *cellv = eb_tab + CT * NPT * L.n_pT;                                    // [CT][2]          Bmax, Bmax - Bmin
   double *pT_s = cellv + CT * 2;                                                 // [n_pT]
 
@@ -157,7 +158,7 @@ cf_shift_kernel(const HotParams hp)
       for (int w = threadIdx.x; w < CT * NYT * NPT; w += blockDim.x) {             // pair table, as in cf_kernel
         const int c = w / (NYT * NPT), r = w - c * (NYT * NPT), j = r / NPT, k = r - j * NPT;
         const double *yr = Ys + (c * NYT + j) * RY, *pr = Ps + (c * NPT + k) * kRec;
-        pair_tab[w] = fma(pr[4], yr[4], -(pr[3] * yr[3]));
+        pair_tab[(c * NYT + j) * NPP + k] = fma(pr[4], yr[4], -(pr[3] * yr[3]));
       }
     }
     for (int c = warp; c < CT; c += 4) {                                         // e^{-pT (Bmax - B_k)}: one cell per warp-iteration
@@ -214,13 +215,21 @@ cf_shift_kernel(const HotParams hp)
         if (!__any_sync(0xffffffffu, alive)) continue;
         const double cpm = mT * v0.y;
         const double h0 = DF ? mT2 * yr[1].x : 0.0;
-        const double w = yr[2].y;
+        // (the eta weight of a 3+1D slot record is 1: p.dsigma = pT Dp + mT Cp)
+        double pr2[NPP];
+        if (DF) {
+#pragma unroll
+          for (int k = 0; k < NPP; k += 2) {
+            const double2 t2 = *reinterpret_cast<const double2 *>(pair_tab + (c * NYT + j) * NPP + k);
+            pr2[k] = t2.x; pr2[k + 1] = t2.y;
+          }
+        }
         double xs[NPT], pv[NPT], sv[NPT];
 #pragma unroll
         for (int k = 0; k < NPT; k++) {
           xs[k] = a - q[k];
-          pv[k] = fma(w, pd[k], cpm);
-          sv[k] = DF ? fma(mTpT, pair_tab[(c * NYT + j) * NPT + k], h0 + g0[k]) : 0.0;
+          pv[k] = pd[k] + cpm;
+          sv[k] = DF ? fma(mTpT, pr2[k], h0 + g0[k]) : 0.0;
         }
         double *accj = acc + j * NPT;
         if (__builtin_expect(__any_sync(0xffffffffu, alive && xh >= rare_hi), 0)) {
@@ -284,7 +293,7 @@ cudaError_t launch_shift_one(const HotParams &hp, cudaStream_t st, size_t *smem_
   const Layout &L = hp.L;
   const int stage_doubles = L.ct * (NYT * kRec + NPT * kRec + kScal);
   const size_t pipe = (size_t)kStages * stage_doubles * 8 + kStages * 8
-                    + ((size_t)L.ct * NYT * NPT + (size_t)L.ct * NPT * L.n_pT + (size_t)L.ct * 2 + L.n_pT) * 8;
+                    + ((size_t)L.ct * NYT * ((NPT + 1) & ~1) + (size_t)L.ct * NPT * L.n_pT + (size_t)L.ct * 2 + L.n_pT) * 8;
   const size_t smem = std::max(pipe, (hot_epilogue_scratch_bytes(hp, NYT, false, 128) + 15) & ~(size_t)15);
   if (smem_out) *smem_out = smem;
   auto kern = cf_shift_kernel<MODEL, NYT, NPT, MINB>;
