@@ -1044,7 +1044,15 @@ extern "C" int is3d_b200_smooth_spectra_multi(const is3d_flags *fl, const is3d_s
   if (opt_in && opt_in->memory != 0) return fail(IS3D_ERR_ARGUMENT, "the multi-GPU entry point takes host arrays");
   std::lock_guard<std::mutex> lk(g_multi_mutex);
   const int64_t n_bins = (int64_t)sp->n * gr->n_pT * gr->n_phi * gr->n_y;
-  int prev = 0; cudaGetDevice(&prev);
+  struct DeviceGuard {            // whatever path leaves this function, the caller's current device is restored
+    int prev = 0;
+    DeviceGuard() { cudaGetDevice(&prev); }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+  } guard;
+  struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  } ev;
   std::vector<int> rcs(G, IS3D_OK);
   std::vector<std::string> errs(G);
   std::vector<is3d_stats> sts(G);
@@ -1065,19 +1073,19 @@ extern "C" int is3d_b200_smooth_spectra_multi(const is3d_flags *fl, const is3d_s
     });
   }
   for (auto &w : workers) w.join();
-  for (int d = 0; d < G; d++) if (rcs[d]) { cudaSetDevice(prev); return fail(rcs[d], errs[d].c_str()); }
+  for (int d = 0; d < G; d++) if (rcs[d]) return fail(rcs[d], errs[d].c_str());
 
   // ---- the one collective of the path: sum of the spectra arrays over NVLink
-  cudaEvent_t e0, e1;
   CU_CHECK(cudaSetDevice(0));
-  CU_CHECK(cudaEventCreate(&e0)); CU_CHECK(cudaEventCreate(&e1));
+  CU_CHECK(cudaEventCreate(&ev.a)); CU_CHECK(cudaEventCreate(&ev.b));
+  const cudaEvent_t e0 = ev.a, e1 = ev.b;
   CU_CHECK(cudaEventRecord(e0, g_streams[0]));
   int nrc = g_nccl.GroupStart();
   for (int d = 0; d < G && nrc == kNcclSuccess; d++)
     nrc = g_nccl.AllReduce(dev_dN[d], dev_dN[d], (size_t)n_bins, kNcclDouble, kNcclSum, g_comms[d], g_streams[d]);
   const int nrc2 = g_nccl.GroupEnd();
   if (nrc == kNcclSuccess) nrc = nrc2;
-  if (nrc != kNcclSuccess) { cudaSetDevice(prev); return fail(IS3D_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "ncclAllReduce failed"); }
+  if (nrc != kNcclSuccess) { return fail(IS3D_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "ncclAllReduce failed"); }
   CU_CHECK(cudaEventRecord(e1, g_streams[0]));
   std::vector<double> host((size_t)n_bins);
   CU_CHECK(cudaMemcpyAsync(host.data(), dev_dN[0], (size_t)n_bins * 8, cudaMemcpyDeviceToHost, g_streams[0]));
@@ -1086,8 +1094,6 @@ extern "C" int is3d_b200_smooth_spectra_multi(const is3d_flags *fl, const is3d_s
   float ms = 0;
   CU_CHECK(cudaSetDevice(0));
   cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  CU_CHECK(cudaSetDevice(prev));
   if (stats) {
     is3d_stats tot; memset(&tot, 0, sizeof(tot));
     for (int d = 0; d < G; d++) merge_stats(&tot, sts[d]);
