@@ -26,7 +26,9 @@ def test_reference_arm_prints_one_json_line(monkeypatch):
             "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '1']; bench.main()")
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
-    line = json.loads(r.stdout.strip().splitlines()[-1])
+    out_lines = r.stdout.strip().splitlines()
+    assert len(out_lines) == 1, out_lines          # stdout carries the JSON record only (the reference's progress goes to stderr)
+    line = json.loads(out_lines[0])
     assert line["impl"] == "reference" and line["unit"] == "evaluations/s" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] in ("reference", "port")
     # non-zero ranks of a torchrun launch do no work and exit 0
